@@ -1,0 +1,123 @@
+"""CPU tests: the oracle (oracle/) against the golden fixtures recorded from the reference itself
+(tests/golden/make_golden.py), plus the reference's own two assertion blocks restated."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import maskbit_oracle as O
+from oracle import select_oracle as SO
+from maskbit_b200.config import load_config, sampler_kwargs
+
+
+def test_factorization_roundtrip():
+    # reference: modeling/modules/factorization.py:49-67
+    g = torch.Generator().manual_seed(0)
+    tokens = torch.randint(0, 1023, (1, 16), generator=g)
+    s1 = O.split_factorized_tokens(tokens, 1024, 1)
+    assert s1.shape == (1, 16, 1) and s1.dtype == torch.int64
+    assert (tokens == O.combine_factorized_tokens(s1, 1024, 1)).all()
+    s2 = O.split_factorized_tokens(tokens, 1024, 2)
+    assert s2.shape == (1, 16, 2)
+    assert (tokens == O.combine_factorized_tokens(s2, 1024, 2)).all()
+    assert (torch.bitwise_right_shift(tokens, 5) == s2[..., 1]).all()
+    assert (tokens & 31 == s2[..., 0]).all()
+
+
+def test_lfq_bits_roundtrip():
+    # reference: modeling/quantizer/lookup_free.py:146-163
+    idx = torch.arange(1024)
+    bits = O.indices_to_bits(idx, 10)
+    assert bits.shape == (1024, 10)
+    assert set(bits.unique().tolist()) == {-1.0, 1.0}
+    assert (O.bits_to_indices(bits) == idx).all()
+    assert (bits[1] == torch.tensor([1.0] + [-1.0] * 9)).all()  # bit k <-> 2^k
+
+
+def test_mask_schedule_tables():
+    # SURVEY.md 3.2 tables measured from the reference's get_masking_ratio
+    t8 = [int(torch.floor(O.get_masking_ratio((i + 1) / 8, "arccos") * 512)) for i in range(8)]
+    assert t8 == [471, 429, 386, 341, 291, 235, 164, 0]
+    with pytest.raises(ValueError):
+        O.get_masking_ratio(0.5, "bogus")
+    s = [float(O.guidance_scale_at(i, 64, 7.1, "cosine", 3.0)) for i in range(4)]
+    assert s[0] == 0.0 and s[1] == 0.0 and s[2] == 0.0 and s[3] > 0.0
+
+
+@pytest.mark.parametrize("bits", [12, 14])
+def test_forward_matches_reference(bits, golden_dir, synthetic_checkpoints):
+    g = np.load(os.path.join(golden_dir, f"forward_{bits}bit.npz"))
+    gen_sd, _ = synthetic_checkpoints(bits)
+    tok = torch.from_numpy(g["tokens"].astype(np.int64))
+    logits = O.lfq_bert_forward(gen_sd, tok, torch.from_numpy(g["labels"]), torch.from_numpy(g["drop"]))
+    ref = torch.from_numpy(g["logits"])
+    assert logits.shape == ref.shape
+    assert (logits - ref).abs().max().item() <= 2e-5
+
+
+def test_decode_matches_reference(golden_dir, synthetic_checkpoints):
+    g = np.load(os.path.join(golden_dir, "decode_12bit.npz"))
+    _, dec_sd = synthetic_checkpoints(12)
+    img = O.decode_tokens(dec_sd, torch.from_numpy(g["tokens"]))
+    assert (img[0] - torch.from_numpy(g["image0"])).abs().max().item() <= 2e-5
+    assert (img[:, :, ::4, ::4] - torch.from_numpy(g["image_sub"])).abs().max().item() <= 2e-5
+
+
+def test_select_matches_reference_trace(golden_dir):
+    """Both select restatements (torch one in maskbit_oracle, plain C in select_oracle.c) reproduce the
+    reference's per-step predicted tokens bit-exactly from its recorded logits and replayed RNG draws."""
+    g = np.load(os.path.join(golden_dir, "select_12bit.npz"))
+    cfg = load_config("maskbit_generator_12bit")
+    kw = sampler_kwargs(cfg)
+    steps, B = g["tokens"].shape[0], g["tokens"].shape[1]
+    masked_t = torch.full((B, 256, 2), kw["mask_token"])
+    masked_c = masked_t.numpy().copy()
+    for i in range(steps):
+        progress = (i + 1) / steps
+        lc, lu = torch.from_numpy(g["logits"][i]).chunk(2, 0)
+        scale = O.guidance_scale_at(i, steps, kw["guidance_scale"], kw["guidance_annealing"], kw["scale_pow"])
+        mask_len = torch.floor(O.get_masking_ratio(progress, kw["mask_schedule_strategy"]) * 512)
+        q, gum = torch.from_numpy(g["q"][i]), torch.from_numpy(g["g"][i])
+        pred_t, masked_t = O.select_step(lc, lu, scale, kw["softmax_temperature"], q, gum,
+                                         kw["randomize_temperature"] * (1 - progress), mask_len, masked_t, kw["mask_token"])
+        ref = g["tokens"][i].astype(np.int64)
+        assert np.array_equal(pred_t.numpy(), ref), f"torch select oracle diverges at step {i}"
+        pred_c, masked_c, k = SO.select_step(lc.numpy(), lu.numpy(), float(scale), kw["softmax_temperature"], q.numpy(),
+                                             gum.numpy(), kw["randomize_temperature"], 1 - progress, float(mask_len),
+                                             masked_c, kw["mask_token"])
+        assert np.array_equal(pred_c, ref), f"C select oracle diverges at step {i}"
+        assert np.array_equal(masked_c, masked_t.numpy()), f"C re-mask differs at step {i}"
+        if i < steps - 1:
+            assert (masked_c == kw["mask_token"]).reshape(B, -1).sum(1).tolist() == [k] * B
+
+
+def test_c_math_kernels():
+    L = SO.lib()
+    xs = np.concatenate([-np.logspace(-6, math.log10(86.9), 400), [0.0, -87.5, -200.0]]).astype(np.float32)
+    for x in xs:
+        got, want = L.mbo_expf(float(x)), math.exp(float(x))
+        if x < -87:
+            assert got == 0.0
+        else:
+            assert abs(got - want) <= 3e-7 * want + 1e-45
+    ps = np.concatenate([np.logspace(-44, 0, 500), [1.0, 0.5, 0.70710678]]).astype(np.float32)
+    for p in ps:
+        got, want = L.mbo_logf(float(p)), math.log(float(p))
+        assert abs(got - want) <= 3e-7 * abs(want) + 2e-7
+    assert L.mbo_logf(0.0) == -math.inf
+
+
+def test_sample_config1_matches_reference(golden_dir, synthetic_checkpoints):
+    """BASELINE config #1 (B=4, 8 steps, CFG cosine): the oracle's free-running sampler reproduces the reference's
+    per-step tokens exactly and its pixels to 2e-5."""
+    g = np.load(os.path.join(golden_dir, "sample_12bit.npz"))
+    gen_sd, dec_sd = synthetic_checkpoints(12)
+    cfg = load_config("maskbit_generator_12bit")
+    kw = dict(sampler_kwargs(cfg), num_steps=8)
+    torch.manual_seed(1234)
+    img, trace = O.sample(gen_sd, dec_sd, 4, torch.from_numpy(g["labels"]), **kw)
+    assert np.array_equal(torch.stack(trace).numpy(), g["tokens"].astype(np.int64))
+    assert (img[0] - torch.from_numpy(g["image0"])).abs().max().item() <= 2e-5
+    assert (img[:, :, ::4, ::4] - torch.from_numpy(g["image_sub"])).abs().max().item() <= 2e-5
