@@ -1,0 +1,784 @@
+// C ABI of the B200-native MaskBit sampling path (declared in include/maskbit_b200.h) and the host-side
+// orchestration: checkpoint packing, workspace, kernel launches for LFQBert.forward / select / decode_tokens / sample.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/maskbit_b200.h"
+#include "attention.cuh"
+#include "decoder.cuh"
+#include "embed_ln.cuh"
+#include "gemm_tcgen05.cuh"
+#include "select.cuh"
+
+using namespace mb;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU_TRY(expr)                                                                                         \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess) return fail(MB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+    } while (0)
+#define MB_TRY(expr)            \
+    do {                        \
+        int _r = (expr);        \
+        if (_r != 0) return _r; \
+    } while (0)
+
+extern "C" const char* mb_last_error(void) { return g_err.c_str(); }
+extern "C" const char* mb_version(void) { return "maskbit_b200 0.1 sm_100a"; }
+
+// ------------------------------------------------------------------------------------------------ TMA descriptors
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// bf16 row-major [rows, cols] (cols contiguous), box = 64 columns (128 B, one swizzle atom) x box_rows
+static int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(MB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu", (int)r,
+                                       (unsigned long long)rows, (unsigned long long)cols);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ small kernels
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+__global__ void transpose_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // in [rows, cols] -> out [cols, rows]
+    if (i < (size_t)rows * cols) { int r = (int)(i / cols), c = (int)(i % cols); out[(size_t)c * rows + r] = in[i]; }
+}
+// conv weight fp32 [Cout][Cin][kh][kw] -> split bf16 hi/lo [Cout][tap*Cin + c]
+__global__ void pack_conv_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                 int cout, int cin, int taps) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)cout * cin * taps;
+    if (i >= total) return;
+    int tap = (int)(i % taps);
+    int c = (int)((i / taps) % cin);
+    int o = (int)(i / ((size_t)taps * cin));
+    float v = w[i];
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    size_t d = (size_t)o * taps * cin + (size_t)tap * cin + c;
+    hi[d] = h; lo[d] = l;
+}
+// conv_in weight [C][bits][3][3] -> [tap][bit][C]
+__global__ void pack_conv_in_kernel(const float* __restrict__ w, float* __restrict__ out, int C, int bits) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)C * bits * 9) return;
+    int tap = (int)(i % 9), k = (int)((i / 9) % bits), c = (int)(i / (9 * (size_t)bits));
+    out[((size_t)tap * bits + k) * C + c] = w[i];
+}
+// conv_out weight [3][C][3][3] -> [tap][C][4]
+__global__ void pack_conv_out_kernel(const float* __restrict__ w, float* __restrict__ out, int C) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)9 * C * 4) return;
+    int o = (int)(i % 4), c = (int)((i / 4) % C), tap = (int)(i / (4 * (size_t)C));
+    out[i] = o < 3 ? w[((size_t)o * C + c) * 9 + tap] : 0.f;
+}
+__global__ void combine_tokens_kernel(const int64_t* __restrict__ tok, int64_t* __restrict__ out, size_t n, int splits, int shift) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t v = 0;
+    for (int g = 0; g < splits; ++g) v += tok[i * splits + g] << (g * shift);   // factorization.py:20-22
+    out[i] = v;
+}
+__global__ void fill_i64_kernel(int64_t* p, size_t n, int64_t v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ handle
+struct DevTensor { float* ptr = nullptr; std::vector<int64_t> shape; size_t numel = 0; };
+
+struct Linear {
+    __nv_bfloat16* w = nullptr; float* b = nullptr; int N = 0, K = 0, BN = 0; CUtensorMap tm;
+};
+struct LNW { float* g = nullptr; float* b = nullptr; };
+struct Layer { Linear qkv, out, up, down; LNW ln1, ln2; };
+struct ConvW { __nv_bfloat16* hi = nullptr; __nv_bfloat16* lo = nullptr; float* bias = nullptr; int cin = 0, cout = 0, taps = 0; };
+struct GNW { float* g = nullptr; float* b = nullptr; int C = 0; };
+struct ResBlockW { GNW n1, n2; ConvW c1, c2, nin; bool has_nin = false; };
+struct StageW { std::vector<ResBlockW> blocks; bool has_up = false; ConvW up; };
+
+struct mb_handle {
+    mb_config cfg;
+    int device = 0, num_sms = 148;
+    int64_t launches = 0;
+    std::map<std::string, DevTensor> staged[2];
+    bool finalized[2] = {false, false};
+    std::vector<void*> allocs;  // everything cudaMalloc'ed for weights (freed in destroy)
+    // generator
+    int bits = 0, eff_bits = 0, V = 0, S = 0;  // S = seq_len + 1
+    float *w_in_t = nullptr, *b_in = nullptr, *class_emb = nullptr, *pos = nullptr;
+    LNW ln_first, ln_head;
+    std::vector<Layer> layers;
+    Linear head, pred;
+    // generator workspace
+    int cap_seqs = 0; size_t cap_rows = 0;
+    __nv_bfloat16 *x = nullptr, *qkv = nullptr, *att = nullptr, *hmid = nullptr;
+    float* pre = nullptr;
+    CUtensorMap tm_x, tm_att, tm_hmid;
+    // sampler workspace
+    int cap_sample_B = 0;
+    int64_t *tok_a = nullptr, *tok_b = nullptr, *pred_buf = nullptr, *combined = nullptr;
+    float* logits_ws = nullptr; uint8_t* drop_ws = nullptr;
+    // decoder
+    float *cin_w = nullptr, *cin_b = nullptr, *cout_w = nullptr, *cout_b = nullptr;
+    int dec_c0 = 0, dec_cl = 0;
+    std::vector<ResBlockW> mid;
+    std::vector<StageW> ups;
+    GNW norm_out;
+    int dec_cap = 0;
+    float *dx = nullptr, *dt1 = nullptr, *dt2 = nullptr, *gn_scale = nullptr, *gn_shift = nullptr;
+    double2* gn_partial = nullptr;
+};
+
+template <typename T>
+static int dev_alloc(mb_handle* h, T** p, size_t count, bool track = true) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
+    if (e != cudaSuccess) return fail(MB_ERR_CUDA, "cudaMalloc(%zu bytes) -> %s", count * sizeof(T), cudaGetErrorString(e));
+    if (track) h->allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return 0;
+}
+
+extern "C" int mb_create(const mb_config* cfg, mb_handle** out) {
+    if (!cfg || !out) return fail(MB_ERR_INVALID, "mb_create: null argument");
+    if (cfg->hidden_dim != 1024) return fail(MB_ERR_INVALID, "hidden_dim %d unsupported (row kernels are built for 1024)", cfg->hidden_dim);
+    if (cfg->heads <= 0 || cfg->hidden_dim / cfg->heads != 64) return fail(MB_ERR_INVALID, "head dim must be 64");
+    if (cfg->use_prenorm) return fail(MB_ERR_INVALID, "use_prenorm=True is not implemented (no shipped config uses it)");
+    if (cfg->codebook_splits < 1 || cfg->token_bits % cfg->codebook_splits) return fail(MB_ERR_INVALID, "token_bits must divide by codebook_splits");
+    const int V = 1 << (cfg->token_bits / cfg->codebook_splits);
+    if (V < 32 || V > 512) return fail(MB_ERR_INVALID, "per-group vocabulary %d unsupported (32..512)", V);
+    if (cfg->seq_len + 1 > ATT_MAXS || ((cfg->seq_len + 1) % 64) > 16) return fail(MB_ERR_INVALID, "seq_len %d unsupported by the attention kernel", cfg->seq_len);
+    if (cfg->mlp_dim % 256 || cfg->dec_num_resolutions > 8) return fail(MB_ERR_INVALID, "bad mlp_dim / num_resolutions");
+    int dev = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) return fail(MB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+    mb_handle* h = new mb_handle();
+    h->cfg = *cfg;
+    h->device = dev;
+    h->num_sms = prop.multiProcessorCount;
+    h->bits = cfg->token_bits;
+    h->eff_bits = cfg->token_bits / cfg->codebook_splits;
+    h->V = V;
+    h->S = cfg->seq_len + 1;
+    *out = h;
+    return 0;
+}
+
+static void free_ws(mb_handle* h) {
+    void* ps[] = {h->x, h->qkv, h->att, h->hmid, h->pre};
+    for (void* p : ps) if (p) cudaFree(p);
+    h->x = h->qkv = h->att = h->hmid = nullptr; h->pre = nullptr; h->cap_seqs = 0;
+}
+static void free_sample_ws(mb_handle* h) {
+    void* ps[] = {h->tok_a, h->tok_b, h->pred_buf, h->combined, h->logits_ws, h->drop_ws};
+    for (void* p : ps) if (p) cudaFree(p);
+    h->tok_a = h->tok_b = h->pred_buf = h->combined = nullptr; h->logits_ws = nullptr; h->drop_ws = nullptr; h->cap_sample_B = 0;
+}
+static void free_dec_ws(mb_handle* h) {
+    void* ps[] = {h->dx, h->dt1, h->dt2, h->gn_scale, h->gn_shift, h->gn_partial};
+    for (void* p : ps) if (p) cudaFree(p);
+    h->dx = h->dt1 = h->dt2 = h->gn_scale = h->gn_shift = nullptr; h->gn_partial = nullptr; h->dec_cap = 0;
+}
+
+extern "C" void mb_destroy(mb_handle* h) {
+    if (!h) return;
+    cudaDeviceSynchronize();
+    for (int m = 0; m < 2; ++m) for (auto& kv : h->staged[m]) cudaFree(kv.second.ptr);
+    for (void* p : h->allocs) cudaFree(p);
+    free_ws(h); free_sample_ws(h); free_dec_ws(h);
+    delete h;
+}
+
+extern "C" int64_t mb_launch_count(mb_handle* h) { return h ? h->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------ checkpoint loading
+extern "C" int mb_set_tensor(mb_handle* h, int model, const char* name, const float* data, const int64_t* shape, int ndim,
+                             int on_device) {
+    if (!h || !name || !data || model < 0 || model > 1) return fail(MB_ERR_INVALID, "mb_set_tensor: bad argument");
+    if (h->finalized[model]) return fail(MB_ERR_STATE, "model %d already finalized", model);
+    DevTensor t;
+    t.numel = 1;
+    for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); t.numel *= (size_t)shape[i]; }
+    if (model == MB_TOKENIZER && strncmp(name, "encoder.", 8) == 0) return 0;  // encode path not part of this library yet
+    auto it = h->staged[model].find(name);
+    if (it != h->staged[model].end()) { cudaFree(it->second.ptr); h->staged[model].erase(it); }
+    CU_TRY(cudaMalloc(&t.ptr, t.numel * sizeof(float) + 16));
+    CU_TRY(cudaMemcpy(t.ptr, data, t.numel * sizeof(float), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    h->staged[model][name] = t;
+    return 0;
+}
+
+static int take(mb_handle* h, int model, const std::string& name, std::vector<int64_t> shape, DevTensor* out) {
+    auto it = h->staged[model].find(name);
+    if (it == h->staged[model].end()) return fail(MB_ERR_MISSING, "strict loading: missing key \"%s\"", name.c_str());
+    if (it->second.shape != shape) {
+        std::string got, want;
+        for (auto v : it->second.shape) got += std::to_string(v) + ",";
+        for (auto v : shape) want += std::to_string(v) + ",";
+        return fail(MB_ERR_INVALID, "size mismatch for %s: checkpoint (%s) vs model (%s)", name.c_str(), got.c_str(), want.c_str());
+    }
+    *out = it->second;
+    return 0;
+}
+static int keep_f32(mb_handle* h, int model, const std::string& name, std::vector<int64_t> shape, float** out) {
+    DevTensor t;
+    MB_TRY(take(h, model, name, shape, &t));
+    h->allocs.push_back(t.ptr);           // ownership moves from staging to the weight set
+    h->staged[model].erase(name);
+    *out = t.ptr;
+    return 0;
+}
+static int pick_bn(int N) { return N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 0)); }
+
+static int make_linear(mb_handle* h, const std::string& wname, const std::string& bname, int N, int K, Linear* L) {
+    DevTensor w;
+    MB_TRY(take(h, MB_GENERATOR, wname, {N, K}, &w));
+    L->N = N; L->K = K; L->BN = pick_bn(N);
+    if (!L->BN || K % 64) return fail(MB_ERR_INVALID, "linear %s: N=%d K=%d not tileable", wname.c_str(), N, K);
+    MB_TRY(dev_alloc(h, &L->w, (size_t)N * K));
+    f32_to_bf16_kernel<<<(unsigned)(((size_t)N * K + 255) / 256), 256>>>(w.ptr, L->w, (size_t)N * K);
+    CU_TRY(cudaGetLastError());
+    MB_TRY(keep_f32(h, MB_GENERATOR, bname, {N}, &L->b));
+    MB_TRY(make_tmap_bf16(&L->tm, L->w, N, K, L->BN));
+    CU_TRY(cudaDeviceSynchronize());
+    cudaFree(w.ptr);
+    h->staged[MB_GENERATOR].erase(wname);
+    return 0;
+}
+
+static int finalize_generator(mb_handle* h) {
+    const mb_config& c = h->cfg;
+    const int D = c.hidden_dim;
+    DevTensor t;
+    MB_TRY(take(h, MB_GENERATOR, "input_proj.weight", {D, h->bits}, &t));
+    MB_TRY(dev_alloc(h, &h->w_in_t, (size_t)D * h->bits));
+    transpose_f32_kernel<<<(D * h->bits + 255) / 256, 256>>>(t.ptr, h->w_in_t, D, h->bits);
+    CU_TRY(cudaDeviceSynchronize());
+    cudaFree(t.ptr); h->staged[MB_GENERATOR].erase("input_proj.weight");
+    MB_TRY(keep_f32(h, MB_GENERATOR, "input_proj.bias", {D}, &h->b_in));
+    MB_TRY(keep_f32(h, MB_GENERATOR, "class_emb.weight", {c.nclass + 1, D}, &h->class_emb));
+    MB_TRY(keep_f32(h, MB_GENERATOR, "pos_emb", {1, h->S, D}, &h->pos));
+    MB_TRY(keep_f32(h, MB_GENERATOR, "first_layer.0.weight", {D}, &h->ln_first.g));
+    MB_TRY(keep_f32(h, MB_GENERATOR, "first_layer.0.bias", {D}, &h->ln_first.b));
+    h->layers.resize(c.depth);
+    for (int l = 0; l < c.depth; ++l) {
+        const std::string p = "transformer.layers." + std::to_string(l) + ".";
+        Layer& L = h->layers[l];
+        MB_TRY(make_linear(h, p + "0.mha.in_proj_weight", p + "0.mha.in_proj_bias", 3 * D, D, &L.qkv));
+        MB_TRY(make_linear(h, p + "0.mha.out_proj.weight", p + "0.mha.out_proj.bias", D, D, &L.out));
+        MB_TRY(keep_f32(h, MB_GENERATOR, p + "0.norm.weight", {D}, &L.ln1.g));
+        MB_TRY(keep_f32(h, MB_GENERATOR, p + "0.norm.bias", {D}, &L.ln1.b));
+        MB_TRY(make_linear(h, p + "1.net.0.weight", p + "1.net.0.bias", c.mlp_dim, D, &L.up));
+        MB_TRY(make_linear(h, p + "1.net.2.weight", p + "1.net.2.bias", D, c.mlp_dim, &L.down));
+        MB_TRY(keep_f32(h, MB_GENERATOR, p + "1.norm.weight", {D}, &L.ln2.g));
+        MB_TRY(keep_f32(h, MB_GENERATOR, p + "1.norm.bias", {D}, &L.ln2.b));
+    }
+    MB_TRY(make_linear(h, "last_layer.0.weight", "last_layer.0.bias", D, D, &h->head));
+    MB_TRY(keep_f32(h, MB_GENERATOR, "last_layer.2.weight", {D}, &h->ln_head.g));
+    MB_TRY(keep_f32(h, MB_GENERATOR, "last_layer.2.bias", {D}, &h->ln_head.b));
+    MB_TRY(make_linear(h, "prediction_layer.weight", "prediction_layer.bias", c.codebook_splits * h->V, D, &h->pred));
+    // buffers of the reference module that carry no information for this path
+    auto it = h->staged[MB_GENERATOR].find("bits_to_indices");
+    if (it != h->staged[MB_GENERATOR].end()) { cudaFree(it->second.ptr); h->staged[MB_GENERATOR].erase(it); }
+    if (!h->staged[MB_GENERATOR].empty())
+        return fail(MB_ERR_UNEXPECTED, "strict loading: unexpected key \"%s\"", h->staged[MB_GENERATOR].begin()->first.c_str());
+    return 0;
+}
+
+static int make_conv(mb_handle* h, const std::string& name, int cout, int cin, int k, bool bias, ConvW* W) {
+    DevTensor t;
+    MB_TRY(take(h, MB_TOKENIZER, name + ".weight", {cout, cin, k, k}, &t));
+    W->cin = cin; W->cout = cout; W->taps = k * k;
+    if (cin % CV_BK || cout % CV_BN) return fail(MB_ERR_INVALID, "conv %s: channels %d->%d not tileable", name.c_str(), cin, cout);
+    const size_t n = (size_t)cout * cin * k * k;
+    MB_TRY(dev_alloc(h, &W->hi, n));
+    MB_TRY(dev_alloc(h, &W->lo, n));
+    pack_conv_kernel<<<(unsigned)((n + 255) / 256), 256>>>(t.ptr, W->hi, W->lo, cout, cin, k * k);
+    CU_TRY(cudaDeviceSynchronize());
+    cudaFree(t.ptr); h->staged[MB_TOKENIZER].erase(name + ".weight");
+    if (bias) MB_TRY(keep_f32(h, MB_TOKENIZER, name + ".bias", {cout}, &W->bias));
+    return 0;
+}
+static int make_gn(mb_handle* h, const std::string& name, int C, GNW* g) {
+    g->C = C;
+    MB_TRY(keep_f32(h, MB_TOKENIZER, name + ".weight", {C}, &g->g));
+    MB_TRY(keep_f32(h, MB_TOKENIZER, name + ".bias", {C}, &g->b));
+    return 0;
+}
+static int make_block(mb_handle* h, const std::string& p, int cin, int cout, ResBlockW* rb) {
+    MB_TRY(make_gn(h, p + "norm1", cin, &rb->n1));
+    MB_TRY(make_conv(h, p + "conv1", cout, cin, 3, false, &rb->c1));
+    MB_TRY(make_gn(h, p + "norm2", cout, &rb->n2));
+    MB_TRY(make_conv(h, p + "conv2", cout, cout, 3, false, &rb->c2));
+    rb->has_nin = cin != cout;
+    if (rb->has_nin) MB_TRY(make_conv(h, p + "nin_shortcut", cout, cout, 1, false, &rb->nin));
+    return 0;
+}
+
+static int finalize_tokenizer(mb_handle* h) {
+    const mb_config& c = h->cfg;
+    const int hc = c.dec_hidden_channels, nr = c.dec_num_resolutions;
+    const int block_in = hc * c.dec_channel_mult[nr - 1];
+    h->dec_c0 = block_in;
+    DevTensor t;
+    MB_TRY(take(h, MB_TOKENIZER, "decoder.conv_in.weight", {block_in, h->bits, 3, 3}, &t));
+    MB_TRY(dev_alloc(h, &h->cin_w, (size_t)block_in * h->bits * 9));
+    pack_conv_in_kernel<<<(block_in * h->bits * 9 + 255) / 256, 256>>>(t.ptr, h->cin_w, block_in, h->bits);
+    CU_TRY(cudaDeviceSynchronize());
+    cudaFree(t.ptr); h->staged[MB_TOKENIZER].erase("decoder.conv_in.weight");
+    MB_TRY(keep_f32(h, MB_TOKENIZER, "decoder.conv_in.bias", {block_in}, &h->cin_b));
+    h->mid.resize(c.dec_num_res_blocks);
+    for (int r = 0; r < c.dec_num_res_blocks; ++r)
+        MB_TRY(make_block(h, "decoder.mid.res_blocks." + std::to_string(r) + ".", block_in, block_in, &h->mid[r]));
+    h->ups.resize(nr);
+    int cout = block_in;
+    for (int j = 0; j < nr; ++j) {
+        const int lvl = nr - 1 - j;
+        const int mult_hi = lvl + 1 < nr ? c.dec_channel_mult[lvl + 1] : c.dec_channel_mult[nr - 1];
+        const int cin = hc * mult_hi;
+        cout = hc * c.dec_channel_mult[lvl];
+        StageW& st = h->ups[j];
+        st.blocks.resize(c.dec_num_res_blocks);
+        for (int r = 0; r < c.dec_num_res_blocks; ++r)
+            MB_TRY(make_block(h, "decoder.up." + std::to_string(j) + ".res_blocks." + std::to_string(r) + ".", r == 0 ? cin : cout, cout, &st.blocks[r]));
+        st.has_up = lvl > 0;
+        if (st.has_up) MB_TRY(make_conv(h, "decoder.up." + std::to_string(j) + ".upsample_conv", cout, cout, 3, true, &st.up));
+    }
+    h->dec_cl = cout;
+    MB_TRY(make_gn(h, "decoder.norm_out", cout, &h->norm_out));
+    if (c.num_channels != 3) return fail(MB_ERR_INVALID, "num_channels must be 3");
+    MB_TRY(take(h, MB_TOKENIZER, "decoder.conv_out.weight", {3, cout, 3, 3}, &t));
+    MB_TRY(dev_alloc(h, &h->cout_w, (size_t)9 * cout * 4));
+    pack_conv_out_kernel<<<(9 * cout * 4 + 255) / 256, 256>>>(t.ptr, h->cout_w, cout);
+    CU_TRY(cudaDeviceSynchronize());
+    cudaFree(t.ptr); h->staged[MB_TOKENIZER].erase("decoder.conv_out.weight");
+    MB_TRY(keep_f32(h, MB_TOKENIZER, "decoder.conv_out.bias", {3}, &h->cout_b));
+    for (const char* nm : {"quantize.bits_to_indices", "quantize.codebook"}) {   // implicit codebook: bit k <-> 2^k
+        auto it = h->staged[MB_TOKENIZER].find(nm);
+        if (it == h->staged[MB_TOKENIZER].end()) return fail(MB_ERR_MISSING, "strict loading: missing key \"%s\"", nm);
+        cudaFree(it->second.ptr); h->staged[MB_TOKENIZER].erase(it);
+    }
+    if (!h->staged[MB_TOKENIZER].empty())
+        return fail(MB_ERR_UNEXPECTED, "strict loading: unexpected key \"%s\"", h->staged[MB_TOKENIZER].begin()->first.c_str());
+    return 0;
+}
+
+template <int BN, int EPI>
+static int set_gemm_attr() {
+    CU_TRY(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES));
+    return 0;
+}
+template <int BN>
+static int set_gemm_attr_bn() {
+    MB_TRY((set_gemm_attr<BN, 0>())); MB_TRY((set_gemm_attr<BN, 1>())); MB_TRY((set_gemm_attr<BN, 2>()));
+    MB_TRY((set_gemm_attr<BN, 3>())); MB_TRY((set_gemm_attr<BN, 4>()));
+    return 0;
+}
+static int init_kernel_attrs() {
+    static bool done = false;
+    if (done) return 0;
+    MB_TRY(set_gemm_attr_bn<64>()); MB_TRY(set_gemm_attr_bn<128>()); MB_TRY(set_gemm_attr_bn<256>());
+    CU_TRY(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ATT_MAXS * ATT_LDS * 2));
+    CU_TRY(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_BYTES));
+    done = true;
+    return 0;
+}
+
+extern "C" int mb_finalize(mb_handle* h, int model) {
+    if (!h || model < 0 || model > 1) return fail(MB_ERR_INVALID, "mb_finalize: bad argument");
+    if (h->finalized[model]) return fail(MB_ERR_STATE, "model %d already finalized", model);
+    MB_TRY(init_kernel_attrs());
+    MB_TRY(model == MB_GENERATOR ? finalize_generator(h) : finalize_tokenizer(h));
+    CU_TRY(cudaDeviceSynchronize());
+    h->finalized[model] = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM launch
+template <int BN>
+static int launch_gemm_bn(mb_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int epi, int num_sms,
+                          cudaStream_t st) {
+    const int tiles = ((p.M + 127) / 128) * (p.N / BN);
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    const int smem = GemmCfg<BN>::SMEM_BYTES;
+    switch (epi) {
+        case 0: gemm_bf16_tcgen05_kernel<BN, 0><<<grid, 384, smem, st>>>(ta, tb, p); break;
+        case 1: gemm_bf16_tcgen05_kernel<BN, 1><<<grid, 384, smem, st>>>(ta, tb, p); break;
+        case 2: gemm_bf16_tcgen05_kernel<BN, 2><<<grid, 384, smem, st>>>(ta, tb, p); break;
+        case 3: gemm_bf16_tcgen05_kernel<BN, 3><<<grid, 384, smem, st>>>(ta, tb, p); break;
+        case 4: gemm_bf16_tcgen05_kernel<BN, 4><<<grid, 384, smem, st>>>(ta, tb, p); break;
+        default: return fail(MB_ERR_INVALID, "bad epilogue %d", epi);
+    }
+    CU_TRY(cudaGetLastError());
+    if (h) h->launches++;
+    return 0;
+}
+static int launch_gemm(mb_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, int BN, const GemmParams& p, int epi,
+                       int num_sms, cudaStream_t st) {
+    if (p.K % 64 || p.N % BN) return fail(MB_ERR_INVALID, "gemm shape M=%d N=%d K=%d BN=%d", p.M, p.N, p.K, BN);
+    if (BN == 256) return launch_gemm_bn<256>(h, ta, tb, p, epi, num_sms, st);
+    if (BN == 128) return launch_gemm_bn<128>(h, ta, tb, p, epi, num_sms, st);
+    if (BN == 64) return launch_gemm_bn<64>(h, ta, tb, p, epi, num_sms, st);
+    return fail(MB_ERR_INVALID, "bad BN %d", BN);
+}
+static int run_linear(mb_handle* h, const CUtensorMap& ta, const Linear& L, int M, int epi, const __nv_bfloat16* residual,
+                      void* out, int ldo, cudaStream_t st, int seq_in = 0, int seq_out = 0) {
+    GemmParams p;
+    p.M = M; p.N = L.N; p.K = L.K; p.bias = L.b; p.residual = residual; p.ldr = L.N; p.out = out; p.ldo = ldo;
+    p.seq_in = seq_in; p.seq_out = seq_out;
+    return launch_gemm(h, ta, L.tm, L.BN, p, epi, h->num_sms, st);
+}
+
+// ------------------------------------------------------------------------------------------------ generator forward
+static int ensure_ws(mb_handle* h, int n_seq) {
+    if (n_seq <= h->cap_seqs) return 0;
+    CU_TRY(cudaDeviceSynchronize());
+    free_ws(h);
+    const size_t rows = (((size_t)n_seq * h->S + 127) / 128) * 128;
+    const int D = h->cfg.hidden_dim;
+    MB_TRY(dev_alloc(h, &h->x, rows * D, false));
+    MB_TRY(dev_alloc(h, &h->qkv, rows * 3 * D, false));
+    MB_TRY(dev_alloc(h, &h->att, rows * D, false));
+    MB_TRY(dev_alloc(h, &h->hmid, rows * h->cfg.mlp_dim, false));
+    MB_TRY(dev_alloc(h, &h->pre, rows * D, false));
+    CU_TRY(cudaMemset(h->x, 0, rows * D * 2));
+    CU_TRY(cudaMemset(h->att, 0, rows * D * 2));
+    CU_TRY(cudaMemset(h->hmid, 0, rows * h->cfg.mlp_dim * 2));
+    MB_TRY(make_tmap_bf16(&h->tm_x, h->x, rows, D, 128));
+    MB_TRY(make_tmap_bf16(&h->tm_att, h->att, rows, D, 128));
+    MB_TRY(make_tmap_bf16(&h->tm_hmid, h->hmid, rows, h->cfg.mlp_dim, 128));
+    h->cap_seqs = n_seq; h->cap_rows = rows;
+    return 0;
+}
+
+static int forward_impl(mb_handle* h, const int64_t* tokens, int n_token_rows, const int64_t* labels, int n_label_rows,
+                        const uint8_t* drop, int n_seq, float* logits, cudaStream_t st) {
+    if (!h->finalized[MB_GENERATOR]) return fail(MB_ERR_STATE, "generator weights not loaded (mb_set_tensor + mb_finalize)");
+    if (n_seq <= 0 || n_token_rows <= 0 || n_label_rows <= 0) return fail(MB_ERR_INVALID, "forward: empty batch");
+    MB_TRY(ensure_ws(h, n_seq));
+    const mb_config& c = h->cfg;
+    constexpr int D = 1024;
+    const int M = n_seq * h->S;
+    const float eps = 1e-12f;
+    const int rows_per_blk = 8;
+    const unsigned ln_grid = (unsigned)((M + rows_per_blk - 1) / rows_per_blk);
+    embed_ln_kernel<D><<<ln_grid, 256, 0, st>>>(tokens, n_token_rows, labels, n_label_rows, drop, n_seq, c.seq_len, c.codebook_splits,
+                                                 h->eff_bits, c.nclass, h->w_in_t, h->b_in, h->class_emb, h->pos, h->ln_first.g,
+                                                 h->ln_first.b, eps, h->x);
+    CU_TRY(cudaGetLastError()); h->launches++;
+    const float sl2 = 1.4426950408889634f / sqrtf((float)ATT_HD);
+    for (int l = 0; l < c.depth; ++l) {
+        const Layer& L = h->layers[l];
+        MB_TRY(run_linear(h, h->tm_x, L.qkv, M, EPI_BIAS_BF16, nullptr, h->qkv, 3 * D, st));
+        attention_kernel<<<n_seq * c.heads, ATT_THREADS, 2 * ATT_MAXS * ATT_LDS * 2, st>>>(h->qkv, h->att, h->S, D, c.heads, sl2);
+        CU_TRY(cudaGetLastError()); h->launches++;
+        MB_TRY(run_linear(h, h->tm_att, L.out, M, EPI_BIAS_RES_F32, h->x, h->pre, D, st));
+        layernorm_kernel<D><<<ln_grid, 256, 0, st>>>(h->pre, L.ln1.g, L.ln1.b, eps, h->x, M);
+        CU_TRY(cudaGetLastError()); h->launches++;
+        MB_TRY(run_linear(h, h->tm_x, L.up, M, EPI_BIAS_GELU_BF16, nullptr, h->hmid, c.mlp_dim, st));
+        MB_TRY(run_linear(h, h->tm_hmid, L.down, M, EPI_BIAS_RES_F32, h->x, h->pre, D, st));
+        layernorm_kernel<D><<<ln_grid, 256, 0, st>>>(h->pre, L.ln2.g, L.ln2.b, eps, h->x, M);
+        CU_TRY(cudaGetLastError()); h->launches++;
+    }
+    MB_TRY(run_linear(h, h->tm_x, h->head, M, 4 /*bias+gelu -> f32*/, nullptr, h->pre, D, st));
+    layernorm_kernel<D><<<ln_grid, 256, 0, st>>>(h->pre, h->ln_head.g, h->ln_head.b, eps, h->att, M);
+    CU_TRY(cudaGetLastError()); h->launches++;
+    MB_TRY(run_linear(h, h->tm_att, h->pred, M, EPI_BIAS_F32_SEQ, nullptr, logits, h->pred.N, st, h->S, c.seq_len));
+    return 0;
+}
+
+extern "C" int mb_generator_forward(mb_handle* h, const int64_t* tokens, int n_token_rows, const int64_t* labels,
+                                    int n_label_rows, const uint8_t* drop, int n_seq, float* logits, mb_stream stream) {
+    if (!h || !tokens || !labels || !logits) return fail(MB_ERR_INVALID, "mb_generator_forward: null argument");
+    return forward_impl(h, tokens, n_token_rows, labels, n_label_rows, drop, n_seq, logits, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ select
+static int select_impl(mb_handle* h, const mb_select_args* a, cudaStream_t st) {
+    SelectParams p;
+    p.logits_c = a->logits_c; p.logits_u = a->logits_u; p.q = a->q; p.gumbel = a->gumbel;
+    p.tokens_in = a->tokens_in; p.predicted = a->predicted; p.tokens_out = a->tokens_out;
+    p.scale = a->scale; p.temperature = a->temperature; p.randomize_temperature = a->randomize_temperature;
+    p.one_minus_progress = a->one_minus_progress; p.mask_len = a->mask_len;
+    p.n = a->n; p.m = a->splits; p.V = a->V; p.seq_stride = a->seq_stride; p.mask_token = a->mask_token;
+    p.seed = a->seed; p.step = a->step;
+    const int slots = a->n * a->splits;
+    if (a->B <= 0 || slots <= 0 || slots > 4096) return fail(MB_ERR_INVALID, "select: B=%d slots=%d", a->B, slots);
+    if (a->tokens_in == a->tokens_out) return fail(MB_ERR_INVALID, "select: tokens_in and tokens_out must be distinct buffers");
+    const size_t smem = ((slots * 4 + 15) & ~15) + (size_t)slots * 8;
+    switch (a->V) {
+        case 32: select_step_kernel<1><<<a->B, 512, smem, st>>>(p); break;
+        case 64: select_step_kernel<2><<<a->B, 512, smem, st>>>(p); break;
+        case 128: select_step_kernel<4><<<a->B, 512, smem, st>>>(p); break;
+        case 256: select_step_kernel<8><<<a->B, 512, smem, st>>>(p); break;
+        case 512: select_step_kernel<16><<<a->B, 512, smem, st>>>(p); break;
+        default: return fail(MB_ERR_INVALID, "select: vocabulary %d unsupported", a->V);
+    }
+    CU_TRY(cudaGetLastError());
+    if (h) h->launches++;
+    return 0;
+}
+extern "C" int mb_select_step(mb_handle* h, const mb_select_args* a, mb_stream stream) {
+    if (!a || !a->logits_c || !a->tokens_in || !a->predicted || !a->tokens_out) return fail(MB_ERR_INVALID, "mb_select_step: null argument");
+    return select_impl(h, a, (cudaStream_t)stream);
+}
+
+extern "C" int mb_combine_tokens(mb_handle* h, const int64_t* tokens, int B, int64_t* combined, mb_stream stream) {
+    if (!h || !tokens || !combined || B <= 0) return fail(MB_ERR_INVALID, "mb_combine_tokens: bad argument");
+    const size_t n = (size_t)B * h->cfg.seq_len;
+    combine_tokens_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(tokens, combined, n, h->cfg.codebook_splits, h->eff_bits);
+    CU_TRY(cudaGetLastError()); h->launches++;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ decoder
+static const int kDecChunk = 32;
+static int ensure_dec_ws(mb_handle* h, int nb) {
+    if (nb <= h->dec_cap) return 0;
+    CU_TRY(cudaDeviceSynchronize());
+    free_dec_ws(h);
+    const mb_config& c = h->cfg;
+    const int P = (int)lround(sqrt((double)c.seq_len));
+    size_t max_elems = 0;
+    int R = P, C = h->dec_c0;
+    max_elems = (size_t)R * R * C;
+    for (size_t j = 0; j < h->ups.size(); ++j) {
+        for (auto& b : h->ups[j].blocks) { size_t e = (size_t)R * R * (b.c1.cin > b.c1.cout ? b.c1.cin : b.c1.cout); if (e > max_elems) max_elems = e; C = b.c1.cout; }
+        if (h->ups[j].has_up) { R *= 2; size_t e = (size_t)R * R * C; if (e > max_elems) max_elems = e; }
+    }
+    MB_TRY(dev_alloc(h, &h->dx, max_elems * nb, false));
+    MB_TRY(dev_alloc(h, &h->dt1, max_elems * nb, false));
+    MB_TRY(dev_alloc(h, &h->dt2, max_elems * nb, false));
+    MB_TRY(dev_alloc(h, &h->gn_scale, (size_t)nb * 1024, false));
+    MB_TRY(dev_alloc(h, &h->gn_shift, (size_t)nb * 1024, false));
+    MB_TRY(dev_alloc(h, &h->gn_partial, (size_t)nb * 64 * 32, false));
+    h->dec_cap = nb;
+    return 0;
+}
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+static int run_gn(mb_handle* h, const float* x, const GNW& g, int nb, int R, cudaStream_t st) {
+    const int HW = R * R;
+    int chunks = HW / 1024; if (chunks < 1) chunks = 1; if (chunks > 64) chunks = 64;
+    gn_partial_kernel<<<dim3(chunks, nb), 256, 0, st>>>(x, h->gn_partial, HW, g.C, chunks);
+    CU_TRY(cudaGetLastError()); h->launches++;
+    gn_finalize_kernel<<<nb, 256, 0, st>>>(h->gn_partial, g.g, g.b, h->gn_scale, h->gn_shift, HW, g.C, chunks, 1e-6f);
+    CU_TRY(cudaGetLastError()); h->launches++;
+    return 0;
+}
+static int run_conv(mb_handle* h, const float* in, float* out, const ConvW& w, int nb, int R, bool gn, int up, const float* residual,
+                    cudaStream_t st) {
+    ConvParams p;
+    p.in = in; p.out = out; p.w_hi = w.hi; p.w_lo = w.lo; p.bias = w.bias; p.residual = residual;
+    p.gn_scale = gn ? h->gn_scale : nullptr; p.gn_shift = gn ? h->gn_shift : nullptr;
+    p.B = nb; p.H = R; p.W = R; p.Cin = w.cin; p.Cout = w.cout; p.taps = w.taps; p.up = up; p.logW = ilog2(R); p.logH = ilog2(R);
+    if ((1 << p.logW) != R) return fail(MB_ERR_INVALID, "decoder resolution %d is not a power of two", R);
+    const long long npix = (long long)nb * R * R;
+    dim3 grid((unsigned)((npix + CV_BM - 1) / CV_BM), w.cout / CV_BN);
+    conv_igemm_kernel<<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(p);
+    CU_TRY(cudaGetLastError()); h->launches++;
+    return 0;
+}
+static int run_block(mb_handle* h, const ResBlockW& rb, float*& X, float*& T1, float*& T2, int nb, int R, cudaStream_t st) {
+    MB_TRY(run_gn(h, X, rb.n1, nb, R, st));
+    MB_TRY(run_conv(h, X, T1, rb.c1, nb, R, true, 0, nullptr, st));
+    MB_TRY(run_gn(h, T1, rb.n2, nb, R, st));
+    if (!rb.has_nin) {
+        MB_TRY(run_conv(h, T1, T2, rb.c2, nb, R, true, 0, X, st));              // out = h + x (autoencoder.py:96)
+        float* t = X; X = T2; T2 = t;
+    } else {
+        MB_TRY(run_conv(h, T1, T2, rb.c2, nb, R, true, 0, nullptr, st));
+        MB_TRY(run_conv(h, T2, X, rb.nin, nb, R, false, 0, T2, st));            // out = h + nin(h) (autoencoder.py:93-96 quirk)
+    }
+    return 0;
+}
+
+static int decode_impl(mb_handle* h, const int64_t* tokens, int B, float* images, cudaStream_t st) {
+    if (!h->finalized[MB_TOKENIZER]) return fail(MB_ERR_STATE, "tokenizer weights not loaded (mb_set_tensor + mb_finalize)");
+    const mb_config& c = h->cfg;
+    const int P = (int)lround(sqrt((double)c.seq_len));
+    if (P * P != c.seq_len) return fail(MB_ERR_INVALID, "seq_len %d is not a square", c.seq_len);
+    MB_TRY(ensure_dec_ws(h, B < kDecChunk ? B : kDecChunk));
+    for (int b0 = 0; b0 < B; b0 += kDecChunk) {
+        const int nb = B - b0 < kDecChunk ? B - b0 : kDecChunk;
+        float *X = h->dx, *T1 = h->dt1, *T2 = h->dt2;
+        int R = P;
+        const long long total = (long long)nb * P * P * h->dec_c0;
+        conv_in_tokens_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tokens + (size_t)b0 * c.seq_len, h->cin_w, h->cin_b, X, nb, P, h->bits, h->dec_c0);
+        CU_TRY(cudaGetLastError()); h->launches++;
+        for (auto& rb : h->mid) MB_TRY(run_block(h, rb, X, T1, T2, nb, R, st));
+        for (auto& stg : h->ups) {
+            for (auto& rb : stg.blocks) MB_TRY(run_block(h, rb, X, T1, T2, nb, R, st));
+            if (stg.has_up) {
+                R *= 2;
+                MB_TRY(run_conv(h, X, T1, stg.up, nb, R, false, 1, nullptr, st));   // nearest x2 + conv3x3 (autoencoder.py:224-225)
+                float* t = X; X = T1; T1 = t;
+            }
+        }
+        MB_TRY(run_gn(h, X, h->norm_out, nb, R, st));
+        dim3 grid((R + CO_T - 1) / CO_T, (R + CO_T - 1) / CO_T, nb);
+        conv_out_kernel<<<grid, 256, 0, st>>>(X, h->gn_scale, h->gn_shift, h->cout_w, h->cout_b, images + (size_t)b0 * 3 * R * R, R, R, h->dec_cl);
+        CU_TRY(cudaGetLastError()); h->launches++;
+    }
+    return 0;
+}
+extern "C" int mb_decode_tokens(mb_handle* h, const int64_t* tokens, int B, float* images, mb_stream stream) {
+    if (!h || !tokens || !images || B <= 0) return fail(MB_ERR_INVALID, "mb_decode_tokens: bad argument");
+    return decode_impl(h, tokens, B, images, (cudaStream_t)stream);
+}
+
+extern "C" int mb_postprocess_u8(mb_handle* h, const float* images, int B, uint8_t* out, mb_stream stream) {
+    if (!h || !images || !out || B <= 0) return fail(MB_ERR_INVALID, "mb_postprocess_u8: bad argument");
+    const int R = (int)lround(sqrt((double)h->cfg.seq_len)) << (h->cfg.dec_num_resolutions - 1);
+    const long long total = (long long)B * R * R * 3;
+    postprocess_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(images, out, B, R, R);
+    CU_TRY(cudaGetLastError()); h->launches++;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ sampler
+static int ensure_sample_ws(mb_handle* h, int B) {
+    if (B <= h->cap_sample_B) return 0;
+    CU_TRY(cudaDeviceSynchronize());
+    free_sample_ws(h);
+    const size_t slots = (size_t)h->cfg.seq_len * h->cfg.codebook_splits;
+    MB_TRY(dev_alloc(h, &h->tok_a, B * slots, false));
+    MB_TRY(dev_alloc(h, &h->tok_b, B * slots, false));
+    MB_TRY(dev_alloc(h, &h->pred_buf, B * slots, false));
+    MB_TRY(dev_alloc(h, &h->combined, (size_t)B * h->cfg.seq_len, false));
+    MB_TRY(dev_alloc(h, &h->logits_ws, (size_t)2 * B * slots * h->V, false));
+    MB_TRY(dev_alloc(h, &h->drop_ws, (size_t)2 * B, false));
+    CU_TRY(cudaMemset(h->drop_ws, 0, B));
+    CU_TRY(cudaMemset(h->drop_ws + B, 1, B));
+    h->cap_sample_B = B;
+    return 0;
+}
+
+extern "C" int mb_sample(mb_handle* h, const mb_sample_args* a, mb_stream stream) {
+    if (!h || !a || !a->labels || a->B <= 0 || a->num_steps <= 0 || !a->scale || !a->temperature || !a->one_minus_progress || !a->mask_len)
+        return fail(MB_ERR_INVALID, "mb_sample: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const mb_config& c = h->cfg;
+    const int B = a->B;
+    MB_TRY(ensure_sample_ws(h, B));
+    if (B != h->cap_sample_B) {  // drop flags are laid out for the capacity batch; rebuild for this B
+        CU_TRY(cudaMemsetAsync(h->drop_ws, 0, B, st));
+        CU_TRY(cudaMemsetAsync(h->drop_ws + B, 1, B, st));
+    }
+    const size_t slots = (size_t)c.seq_len * c.codebook_splits;
+    const int64_t mask_token = (int64_t)1 << h->eff_bits;
+    fill_i64_kernel<<<(unsigned)((B * slots + 255) / 256), 256, 0, st>>>(h->tok_a, B * slots, mask_token);   // sampling.py:69
+    CU_TRY(cudaGetLastError()); h->launches++;
+    int64_t *cur = h->tok_a, *nxt = h->tok_b;
+    int64_t* last_pred = h->pred_buf;
+    for (int i = 0; i < a->num_steps; ++i) {
+        const bool guided = a->use_guidance && !(a->skip_zero_scale_uncond && a->scale[i] == 0.0f);
+        const int n_seq = guided ? 2 * B : B;
+        MB_TRY(forward_impl(h, cur, B, a->labels, B, h->drop_ws, n_seq, h->logits_ws, st));
+        mb_select_args s;
+        s.logits_c = h->logits_ws;
+        s.logits_u = guided ? h->logits_ws + (size_t)B * slots * h->V : nullptr;
+        s.q = a->q ? a->q + (size_t)i * B * slots * h->V : nullptr;
+        s.gumbel = a->gumbel ? a->gumbel + (size_t)i * B * slots : nullptr;
+        s.tokens_in = cur;
+        s.predicted = a->trace ? a->trace + (size_t)i * B * slots : h->pred_buf;
+        s.tokens_out = nxt;
+        s.scale = a->scale[i]; s.temperature = a->temperature[i]; s.randomize_temperature = a->randomize_temperature;
+        s.one_minus_progress = a->one_minus_progress[i]; s.mask_len = a->mask_len[i];
+        s.B = B; s.n = c.seq_len; s.splits = c.codebook_splits; s.V = h->V; s.seq_stride = c.seq_len;
+        s.mask_token = mask_token; s.seed = a->seed; s.step = (uint32_t)i;
+        MB_TRY(select_impl(h, &s, st));
+        last_pred = s.predicted;
+        int64_t* t = cur; cur = nxt; nxt = t;
+    }
+    // sampling.py:133-135: the LAST step's predicted tokens (all positions filled) are decoded
+    if (a->images || a->final_tokens) {
+        int64_t* comb = a->final_tokens ? a->final_tokens : h->combined;
+        MB_TRY(mb_combine_tokens(h, last_pred, B, comb, stream));
+        if (a->images) MB_TRY(decode_impl(h, comb, B, a->images, st));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ test hooks
+static int test_num_sms() {
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
+extern "C" int mb_test_gemm(const uint16_t* A, const uint16_t* W, const float* bias, const uint16_t* residual, void* out, int M,
+                            int N, int K, int epi, int seq_in, int seq_out, mb_stream stream) {
+    MB_TRY(init_kernel_attrs());
+    const int BN = pick_bn(N);
+    if (!BN) return fail(MB_ERR_INVALID, "N=%d not tileable", N);
+    CUtensorMap ta, tb;
+    MB_TRY(make_tmap_bf16(&ta, A, M, K, 128));
+    MB_TRY(make_tmap_bf16(&tb, W, N, K, BN));
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K; p.bias = bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = N;
+    p.out = out; p.ldo = N; p.seq_in = seq_in; p.seq_out = seq_out;
+    return launch_gemm(nullptr, ta, tb, BN, p, epi, test_num_sms(), (cudaStream_t)stream);
+}
+extern "C" int mb_test_attention(const uint16_t* qkv, uint16_t* out, int n_seq, int S, int D, int H, mb_stream stream) {
+    MB_TRY(init_kernel_attrs());
+    if (D / H != ATT_HD || S > ATT_MAXS || (S % 64) > 16) return fail(MB_ERR_INVALID, "attention shape unsupported");
+    const float sl2 = 1.4426950408889634f / sqrtf((float)ATT_HD);
+    attention_kernel<<<n_seq * H, ATT_THREADS, 2 * ATT_MAXS * ATT_LDS * 2, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), S, D, H, sl2);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+extern "C" int mb_test_layernorm(const float* in, const float* gamma, const float* beta, float eps, uint16_t* out, int rows, int D,
+                                 mb_stream stream) {
+    if (D != 1024) return fail(MB_ERR_INVALID, "layernorm is built for D=1024");
+    layernorm_kernel<1024><<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(in, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(out), rows);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,209 @@
+// Full (unmasked) multi-head self-attention over the fixed 16x16+1 = 257-token sequence, head_dim 64
+// (reference: nn.MultiheadAttention inside BertAttention, bert.py:84,137 -- softmax(Q K^T / sqrt(64)) V per head).
+//
+// One CTA per (sequence, head).  K and V of the head (257 x 64 bf16 each) stay resident in shared memory for the
+// whole CTA ("KV-free": nothing is cached across calls, every step recomputes all positions).  Each of the 9 warps
+// owns 32 query rows (warp 8 owns the class-token row 256) and runs an online-softmax loop over 64-key chunks:
+// S = Q K^T and O += P V on mma.sync.m16n8k16 bf16 tensor-core tiles with fp32 accumulation, softmax in fp32.
+//
+// Input  qkv  bf16 [n_seq*S, 3*D] (packed in-proj output: q | k | v, head h at columns h*64 of each third)
+// Output out  bf16 [n_seq*S, D]   (heads concatenated, ready for out_proj)
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mb {
+
+constexpr int ATT_HD = 64;          // head dim
+constexpr int ATT_LDS = 72;         // padded smem row (bf16 elements): 144 B rows keep ldmatrix conflict-free
+constexpr int ATT_MAXS = 272;       // 257 keys padded to a multiple of 16
+constexpr int ATT_THREADS = 288;    // 9 warps x 32 query rows
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// One key chunk of NT n-tiles (8 keys each) starting at key k0.  valid_keys = number of real keys in the chunk.
+template <int NT>
+__device__ __forceinline__ void att_chunk(const uint32_t (&qf)[2][4][4], float (&o)[2][8][4], float (&m)[2][2],
+                                          float (&l)[2][2], uint32_t ks_addr, uint32_t vs_addr, int k0, int valid_keys,
+                                          float sl2, int lane) {
+    float s[2][NT][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s[mt][nt][i] = 0.f;
+    // ---- S = Q K^T.  B fragment of (keys n0..n0+7) x (dims 32kp..32kp+31): 4 8x8 matrices, non-transposed.
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {
+            uint32_t b[4];
+            const int key = k0 + nt * 8 + (lane & 7);
+            const int dim = kp * 32 + (lane >> 3) * 8;
+            ldsm_x4(b, ks_addr + (key * ATT_LDS + dim) * 2);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                mma_bf16_16816(s[mt][nt], qf[mt][2 * kp], b[0], b[1]);
+                mma_bf16_16816(s[mt][nt], qf[mt][2 * kp + 1], b[2], b[3]);
+            }
+        }
+    }
+    // ---- mask padded keys, online softmax (rows: [mt][0] = row g, [mt][1] = row g+8)
+    const int t = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int kk = nt * 8 + 2 * t + (i & 1);
+                if (kk >= valid_keys) s[mt][nt][i] = -INFINITY;
+            }
+            mx0 = fmaxf(mx0, fmaxf(s[mt][nt][0], s[mt][nt][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[mt][nt][2], s[mt][nt][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m[mt][0], mx0), mn1 = fmaxf(m[mt][1], mx1);
+        const float a0 = exp2f((m[mt][0] - mn0) * sl2), a1 = exp2f((m[mt][1] - mn1) * sl2);
+        m[mt][0] = mn0; m[mt][1] = mn1;
+        l[mt][0] *= a0; l[mt][1] *= a1;
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) { o[mt][dt][0] *= a0; o[mt][dt][1] *= a0; o[mt][dt][2] *= a1; o[mt][dt][3] *= a1; }
+        const float ms0 = mn0 * sl2, ms1 = mn1 * sl2;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            s[mt][nt][0] = exp2f(fmaf(s[mt][nt][0], sl2, -ms0));
+            s[mt][nt][1] = exp2f(fmaf(s[mt][nt][1], sl2, -ms0));
+            s[mt][nt][2] = exp2f(fmaf(s[mt][nt][2], sl2, -ms1));
+            s[mt][nt][3] = exp2f(fmaf(s[mt][nt][3], sl2, -ms1));
+            l[mt][0] += s[mt][nt][0] + s[mt][nt][1];
+            l[mt][1] += s[mt][nt][2] + s[mt][nt][3];
+        }
+    }
+    // ---- O += P V.  A fragment from the S accumulators (two n-tiles = 16 keys); B = V via transposed ldmatrix.
+#pragma unroll
+    for (int kt = 0; kt < NT / 2; ++kt) {
+        uint32_t pf[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            pf[mt][0] = pack_bf16(s[mt][2 * kt][0], s[mt][2 * kt][1]);
+            pf[mt][1] = pack_bf16(s[mt][2 * kt][2], s[mt][2 * kt][3]);
+            pf[mt][2] = pack_bf16(s[mt][2 * kt + 1][0], s[mt][2 * kt + 1][1]);
+            pf[mt][3] = pack_bf16(s[mt][2 * kt + 1][2], s[mt][2 * kt + 1][3]);
+        }
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
+            uint32_t b[4];
+            const int key = k0 + kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+            const int dim = dp * 16 + (lane >> 4) * 8;
+            ldsm_x4_t(b, vs_addr + (key * ATT_LDS + dim) * 2);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                mma_bf16_16816(o[mt][2 * dp], pf[mt], b[0], b[1]);
+                mma_bf16_16816(o[mt][2 * dp + 1], pf[mt], b[2], b[3]);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int S, int D, int H, float sl2) {
+    extern __shared__ __align__(16) uint8_t att_smem[];
+    __nv_bfloat16* ks = reinterpret_cast<__nv_bfloat16*>(att_smem);
+    __nv_bfloat16* vs = ks + ATT_MAXS * ATT_LDS;
+    const int seq = blockIdx.x / H, head = blockIdx.x % H;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t ld = (size_t)3 * D;
+    const __nv_bfloat16* base = qkv + (size_t)seq * S * ld + head * ATT_HD;
+
+    // K, V -> smem (16-byte chunks, 8 per row); rows >= S zero-filled so padded keys contribute exactly 0 to P V
+    for (int c = threadIdx.x; c < ATT_MAXS * 8; c += ATT_THREADS) {
+        const int r = c >> 3, ch = c & 7;
+        uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+        if (r < S) {
+            kv = __ldg(reinterpret_cast<const uint4*>(base + (size_t)r * ld + D + ch * 8));
+            vv = __ldg(reinterpret_cast<const uint4*>(base + (size_t)r * ld + 2 * D + ch * 8));
+        }
+        *reinterpret_cast<uint4*>(ks + r * ATT_LDS + ch * 8) = kv;
+        *reinterpret_cast<uint4*>(vs + r * ATT_LDS + ch * 8) = vv;
+    }
+    // Q fragments straight from global: [m-tile][k-step][a0..a3]
+    const int g = lane >> 2, t = lane & 3;
+    const int r0 = warp * 32;
+    uint32_t qf[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = r0 + mt * 16 + g + (i & 1) * 8;
+                const int col = kk * 16 + 2 * t + (i >> 1) * 8;
+                qf[mt][kk][i] = row < S ? __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)row * ld + col)) : 0u;
+            }
+    __syncthreads();
+    if (r0 >= S) return;
+
+    float o[2][8][4];
+    float m[2][2], l[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        m[mt][0] = m[mt][1] = -INFINITY;
+        l[mt][0] = l[mt][1] = 0.f;
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[mt][dt][i] = 0.f;
+    }
+    const uint32_t ks_addr = static_cast<uint32_t>(__cvta_generic_to_shared(ks));
+    const uint32_t vs_addr = static_cast<uint32_t>(__cvta_generic_to_shared(vs));
+    const int full_chunks = S / 64;
+#pragma unroll 1
+    for (int c = 0; c < full_chunks; ++c) att_chunk<8>(qf, o, m, l, ks_addr, vs_addr, c * 64, 64, sl2, lane);
+    const int rem = S - full_chunks * 64;   // 1 for S = 257
+    if (rem > 0) {
+        if (rem <= 16) att_chunk<2>(qf, o, m, l, ks_addr, vs_addr, full_chunks * 64, rem, sl2, lane);
+        else att_chunk<8>(qf, o, m, l, ks_addr, vs_addr, full_chunks * 64, rem, sl2, lane);  // needs S <= 272-64+... (checked on host)
+    }
+    // finalize
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        float l0 = l[mt][0], l1 = l[mt][1];
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+        const int row0 = r0 + mt * 16 + g, row1 = row0 + 8;
+        __nv_bfloat16* o0 = out + ((size_t)seq * S + row0) * D + head * ATT_HD + 2 * t;
+        __nv_bfloat16* o1 = out + ((size_t)seq * S + row1) * D + head * ATT_HD + 2 * t;
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) {
+            if (row0 < S) *reinterpret_cast<uint32_t*>(o0 + dt * 8) = pack_bf16(o[mt][dt][0] * i0, o[mt][dt][1] * i0);
+            if (row1 < S) *reinterpret_cast<uint32_t*>(o1 + dt * 8) = pack_bf16(o[mt][dt][2] * i1, o[mt][dt][3] * i1);
+        }
+    }
+}
+
+}  // namespace mb

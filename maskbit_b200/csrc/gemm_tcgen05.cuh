@@ -1,0 +1,210 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  out[M,N] = epilogue(A[M,K] * W[N,K]^T + bias)
+//
+//   A, W     bf16, K contiguous ("K-major"), loaded by TMA (128B swizzle) into a STAGES-deep smem ring
+//   MMA      tcgen05.mma.cta_group::1.kind::f16, M=128 x N=BN x K=16, fp32 accumulators in TMEM,
+//            two accumulator stages (2*BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1
+//   roles    warp 0 lane 0: TMA producer | warp 1 lane 0: MMA issuer | warp 2: TMEM alloc/dealloc
+//            warps 4..11: epilogue (warp%4 = TMEM lane quarter, (warp-4)/4 = column half)
+//   tiles    static round-robin over (m_blk, n_blk) with n fastest, so CTAs resident at the same time share A rows
+//            in L2 and the weight matrix (<= 8 MB) stays L2-resident for the whole launch.
+//
+// This is the kernel behind every Linear of the reference's LFQBert (bert.py:26-31,84,411-417): QKV in-proj,
+// attention out-proj, MLP up (+GELU) / down, head (+GELU) and the prediction layer.
+#pragma once
+#include "ptx.cuh"
+
+namespace mb {
+
+enum EpiMode : int {
+    EPI_BIAS_BF16 = 0,       // out bf16 = acc + bias
+    EPI_BIAS_GELU_BF16 = 1,  // out bf16 = gelu_erf(acc + bias)
+    EPI_BIAS_RES_F32 = 2,    // out fp32 = acc + bias + residual(bf16)         (pre-LayerNorm sum)
+    EPI_BIAS_F32_SEQ = 3,    // out fp32 = acc + bias, rows remapped: drop row seq_in-1 of every sequence (bert.py:503)
+    EPI_BIAS_GELU_F32 = 4,   // out fp32 = gelu_erf(acc + bias)                  (head, before its LayerNorm)
+};
+
+struct GemmParams {
+    int M, N, K;
+    const float* bias;               // [N]
+    const __nv_bfloat16* residual;   // [M, ldr] for EPI_BIAS_RES_F32
+    int ldr;
+    void* out;                       // bf16 or fp32, row stride ldo elements
+    int ldo;
+    int seq_in, seq_out;             // EPI_BIAS_F32_SEQ: rows per sequence in A / kept rows per sequence in out
+};
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int BM = 128, BK = 64;
+    static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // 128 / 256 / 512: powers of two
+    static constexpr int NUM_THREADS = 384;
+    static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(384, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, GemmParams p) {
+    using C = GemmCfg<BN>;
+    constexpr int BM = C::BM, BK = C::BK, STAGES = C::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    // 128B-swizzle atoms are 1024 B: align the ring manually (dynamic smem base is only guaranteed 16 B aligned)
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* base = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    uint8_t* smem_a = base;
+    uint8_t* smem_b = base + STAGES * C::A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + STAGES * (C::A_BYTES + C::B_BYTES));
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_m = (p.M + BM - 1) / BM, num_n = p.N / BN;
+    const int num_tiles = num_m * num_n, num_k = p.K / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_a);
+        tma_prefetch_desc(&tm_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---------------- TMA producer
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / num_n, n_blk = tile % num_n;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], C::A_BYTES + C::B_BYTES);
+                    tma_load_2d(smem_a + stage * C::A_BYTES, &tm_a, &full[stage], kb * BK, m_blk * BM);
+                    tma_load_2d(smem_b + stage * C::B_BYTES, &tm_b, &full[stage], kb * BK, n_blk * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ---------------- MMA issuer
+            constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, BM, BN);
+            int stage = 0; uint32_t phase = 0; uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t a_desc = make_sdesc_k128(smem_u32(smem_a + stage * C::A_BYTES));
+                    const uint64_t b_desc = make_sdesc_k128(smem_u32(smem_b + stage * C::B_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)   // +32 B along K inside the swizzle atom = +2 in (addr >> 4)
+                        umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit(&empty[stage]);      // smem slot reusable once these MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[as]);         // accumulator complete
+            }
+        }
+    } else if (warp >= 4) {  // ---------------- epilogue: TMEM -> registers -> global
+        const int quarter = warp & 3, half = (warp - 4) >> 2;
+        constexpr int COLS_PER_WARP = BN / 2;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int m_blk = tile / num_n, n_blk = tile % num_n;
+            const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
+            const int row = m_blk * BM + quarter * 32 + lane;
+            const bool row_ok = row < p.M;
+            long long out_row = row;
+            bool store_ok = row_ok;
+            if (EPI == EPI_BIAS_F32_SEQ) {
+                const int sq = row / p.seq_in, r = row - sq * p.seq_in;
+                store_ok = row_ok && r < p.seq_out;
+                out_row = (long long)sq * p.seq_out + r;
+            }
+#pragma unroll 1
+            for (int c = 0; c < COLS_PER_WARP; c += 32) {
+                const int col0 = half * COLS_PER_WARP + c;
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + col0, v);
+                tmem_ld_wait();
+                const int n0 = n_blk * BN + col0;
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                    f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
+                    f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+                    f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+                    f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+                }
+                if (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_F32) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+                }
+                if (EPI == EPI_BIAS_RES_F32) {
+                    if (row_ok) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + n0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 r4 = __ldg(rp + j);
+                            const uint32_t w[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                f[j * 8 + 2 * t + 0] += __uint_as_float(w[t] << 16);
+                                f[j * 8 + 2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
+                            }
+                        }
+                    }
+                }
+                if (store_ok) {
+                    if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
+                        uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (size_t)out_row * p.ldo + n0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t w[4];
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                __nv_bfloat162 h = __floats2bfloat162_rn(f[j * 8 + 2 * t], f[j * 8 + 2 * t + 1]);
+                                w[t] = *reinterpret_cast<uint32_t*>(&h);
+                            }
+                            op[j] = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                    } else {
+                        float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + (size_t)out_row * p.ldo + n0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    }
+}
+
+}  // namespace mb
