@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""Benchmark of the MaskBit sampling hot path (BASELINE.json metric: images/sec, 256x256, MaskBit-12bit, 64 steps).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference algorithm on the host CPU cores
+
+One "step" = one pass of the hot path over one batch: sample() of `--batch` images per GPU through all `--sampling-steps`
+decoding steps (CFG double-batch forward + select per step) and the conv decoder.  Prints ONE JSON line (rank 0).
+
+  value      images/s with the labels already resident in HBM, images left in HBM (fp32 NCHW); CUDA events, max over ranks
+  e2e        images/s through the public API with HOST buffers: pinned labels -> H2D, sample(), clamp*255 -> uint8 NHWC
+             (eval_maskbit.py:134-135) -> D2H into pinned memory, every step inside the timed region
+  roofline   the dominant kernel class (MLP up-projection GEMM, tcgen05) timed live with CUDA events on the launch stream
+             over the timed region; algorithmic FLOPs / time vs the measured bf16 peak (MEASURED_PEAKS.json)
+  cpu_baseline  the oracle port of the reference algorithm (oracle/maskbit_oracle.py, torch CPU fp32 ops = what the
+             reference executes) on a bounded sample, on this box's host cores
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# algorithmic FLOPs (SURVEY.md 8d / BASELINE.md 3): 2*MAC, CFG on every step, all 257 rows through the head
+S, D, DEPTH, MLP = 257, 1024, 24, 4096
+
+
+def f_fwd(bits, splits=2):
+    v = 2 ** (bits // splits)
+    per_layer = 2 * S * D * 3 * D + 2 * S * D * D + 4 * S * D * MLP + 4 * S * S * D
+    return DEPTH * per_layer + 2 * 256 * bits * D + 2 * S * D * D + 2 * S * D * (splits * v)
+
+
+F_DEC = {12: 185.97e9, 14: 185.98e9}
+
+
+def f_img(bits, t):
+    return t * 2 * f_fwd(bits) + F_DEC.get(bits, 185.97e9)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(bf16_sustained=p.get("bf16_tflops_sustained"), bf16_burst=p.get("bf16_tflops"), hbm=p.get("hbm_gbs"), source="measured")
+    return dict(bf16_sustained=1400.0, bf16_burst=1590.0, hbm=6650.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, uuid):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", uuid, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference leg
+def cpu_reference_sample(bits, b_cpu, t_cpu, t_full, threads):
+    """The reference algorithm (oracle port: the same torch CPU fp32 ops the reference's modules execute) on a bounded
+    sample: sample() of b_cpu images through t_cpu decoding steps + decode, scaled to t_full steps
+    (every step does identical work: t = t_full * t_step + t_decode)."""
+    import torch
+    from maskbit_b200 import load_config, sampler_kwargs
+    from maskbit_b200.weights import synthetic_conv_vq_state_dict, synthetic_lfq_bert_state_dict
+    from oracle import maskbit_oracle as O
+    torch.set_num_threads(threads)
+    cfg = load_config(f"maskbit_generator_{bits}bit")
+    kw = dict(sampler_kwargs(cfg), num_steps=t_cpu)
+    state = cpu_reference_sample.__dict__.setdefault("state", {})
+    if bits not in state:
+        state[bits] = (synthetic_lfq_bert_state_dict(seed=0, codebook_size=2 ** bits), synthetic_conv_vq_state_dict(seed=0, token_size=bits))
+    gen_sd, dec_sd = state[bits]
+    labels = torch.randint(0, 1000, (b_cpu,), generator=torch.Generator().manual_seed(1234))
+    torch.manual_seed(1234)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        _, trace = O.sample(gen_sd, dec_sd, b_cpu, labels, decode=False, **kw)
+        t1 = time.perf_counter()
+        comb = O.combine_factorized_tokens(trace[-1], 2 ** bits, 2)
+        O.decode_tokens(dec_sd, comb)
+        t2 = time.perf_counter()
+    t_step, t_dec = (t1 - t0) / t_cpu, t2 - t1
+    total = t_full * t_step + t_dec
+    return dict(images_per_s=b_cpu / total, t_step=t_step, t_dec=t_dec, seconds=t2 - t0,
+                sample=f"oracle port of reference sample(): B={b_cpu}, {t_cpu} of {t_full} decoding steps (CFG, fp32) + decode_tokens, "
+                       f"scaled t={t_full}*t_step+t_dec with t_step={t_step:.3f}s t_dec={t_dec:.3f}s")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        cpu_reference_sample(args.bits, args.cpu_batch, 1, args.sampling_steps, threads)
+    vals, secs = [], 0.0
+    last = None
+    for _ in range(args.steps):
+        last = cpu_reference_sample(args.bits, args.cpu_batch, args.cpu_steps, args.sampling_steps, threads)
+        vals.append(last["images_per_s"]); secs += last["seconds"]
+    v = statistics.mean(vals)
+    line = {"impl": "reference", "metric": "images_per_sec", "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * args.batch / v, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": threads, "kind": "port", "sample": last["sample"]},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"MaskBit-Generator {args.bits}-bit, 16x16 tokens x 2 bit-groups, {args.sampling_steps} sampling steps, "
+                        f"batch={args.batch} per GPU, CFG (cosine, 7.1), arccos schedule, 256x256 decode (BASELINE configs[1])",
+            "bits": args.bits, "batch_per_gpu": args.batch, "sampling_steps": args.sampling_steps,
+            "weights": "synthetic (hash-normal, reference state_dict layout)", "labels": "synthetic randint(0,1000)",
+            "noise": "device Philox4x32-10",
+            "l2": "per-step working set (610 MB bf16 weights + >1 GB activations) exceeds the 126 MB L2; no explicit flush",
+            "skip_zero_scale_uncond": bool(args.skip_dead_uncond)}
+
+
+# ------------------------------------------------------------------------------------------------ CUDA arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from maskbit_b200 import build_models, load_config, sample, sampler_kwargs
+    from maskbit_b200.masking import step_tables
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 "
+                             "--master-port P bench.py --gpus N ...")
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = load_config(f"maskbit_generator_{args.bits}bit")
+    kw = dict(sampler_kwargs(cfg), num_steps=args.sampling_steps)
+    tokenizer, gen = build_models(cfg, device=dev)
+    B, T = args.batch, args.sampling_steps
+    # global labels drawn once, sliced contiguously per rank (SURVEY.md 8d config 3 rule)
+    all_labels = torch.randint(0, 1000, (world * B,), generator=torch.Generator().manual_seed(1234))
+    labels_host = all_labels[rank * B:(rank + 1) * B].contiguous().pin_memory()
+    labels_dev = labels_host.to(dev)
+    gathered = torch.empty((world * B, 256, 256, 3), dtype=torch.uint8, device=dev) if world > 1 else None
+    out_host = torch.empty((B, 256, 256, 3), dtype=torch.uint8).pin_memory()
+
+    def one_step(i, e2e):
+        lab = labels_host.to(dev, non_blocking=True) if e2e else labels_dev
+        img, _ = sample(gen, tokenizer, num_samples=B, labels=lab, noise="device", seed=1000 + i, return_trace=False,
+                        skip_zero_scale_uncond=args.skip_dead_uncond, **kw)
+        if e2e or world > 1:
+            u8 = tokenizer.postprocess_uint8(img)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, u8)      # the one collective: finished images (north_star)
+            if e2e:
+                out_host.copy_(u8, non_blocking=True)
+        return img
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(n_steps, e2e, profile):
+        barrier()
+        l0 = gen.launch_count() + tokenizer.launch_count()
+        if profile:
+            gen.profile_enable(True); tokenizer.profile_enable(True)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        ev0.record()
+        for i in range(n_steps):
+            one_step(i, e2e)
+        ev1.record()
+        barrier()
+        wall = time.perf_counter() - w0
+        ms = ev0.elapsed_time(ev1)
+        prof = None
+        if profile:
+            prof = dict(gen.profile_read()); prof.update(tokenizer.profile_read())
+            gen.profile_enable(False); tokenizer.profile_enable(False)
+        launches = gen.launch_count() + tokenizer.launch_count() - l0
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), wall, prof, launches
+
+    for i in range(args.warmup):
+        one_step(i, True)
+    uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    clocks = ClockSampler(uuid if uuid.startswith("GPU-") else "GPU-" + uuid) if rank == 0 else None
+    ms, wall, prof, launches = timed(args.steps, False, True)
+    clk = clocks.stop() if clocks else None
+    ms_e2e, wall_e2e, _, _ = timed(args.steps, True, False)
+
+    if rank == 0:
+        peaks = measured_peaks()
+        n_img = world * B * args.steps
+        value = n_img / (ms / 1000.0)
+        e2e = n_img / (ms_e2e / 1000.0)
+        ms_per_step = ms / args.steps
+        # dominant kernel class: MLP up-projection GEMM [M,1024]x[4096,1024]^T (+bias+GELU), 24 launches per forward
+        scale, _, _, _ = step_tables(T, 512, softmax_temperature=kw["softmax_temperature"], mask_schedule_strategy=kw["mask_schedule_strategy"],
+                                     guidance_scale=kw["guidance_scale"], guidance_annealing=kw["guidance_annealing"],
+                                     scale_pow=kw["scale_pow"], use_sampling_annealing=kw["use_sampling_annealing"])
+        seqs = [B if (args.skip_dead_uncond and s == 0.0) else 2 * B for s in scale]
+        up_flops = args.steps * sum(2.0 * (n * S) * D * MLP * DEPTH for n in seqs)
+        up_ms, up_n = prof.get("gemm_up", (0.0, 0))
+        achieved = up_flops / (up_ms / 1000.0) / 1e12 if up_ms > 0 else None
+        peak = peaks["bf16_sustained"]
+        gpu_ms = sum(v[0] for v in prof.values())
+        breakdown = {k: round(v[0] / gpu_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+        # transformer-step roofline (BASELINE metric "%roofline"): all sampling FLOPs of the job / time vs measured peak
+        job_flops = n_img * f_img(args.bits, T)
+        line = {
+            "metric": "images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": workload_config(args),
+            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": B * 256 * 256 * 3,
+                    "ms_per_step": ms_e2e / args.steps, "wall_s": wall_e2e},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel<256,EPI_BIAS_GELU_BF16> (MLP up GEMM)",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+                         "traffic": None, "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+                         "launches": up_n, "avg_launch_ms": (up_ms / up_n) if up_n else None,
+                         "flops_per_launch": up_flops / up_n if up_n else None},
+            "ms_per_sampling_step": ms_per_step / T,
+            "job_tflops": job_flops / (ms / 1000.0) / 1e12 / world,
+            "job_roofline_frac": job_flops / (ms / 1000.0) / 1e12 / world / peak,
+            "kernel_time_share": breakdown,
+            "wall_s": wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            r = cpu_reference_sample(args.bits, args.cpu_batch, args.cpu_steps, T, threads)
+            line["cpu_baseline"] = {"value": r["images_per_s"], "unit": "images/s", "cores": threads, "kind": "port", "sample": r["sample"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--bits", type=int, default=12)
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--sampling-steps", type=int, default=64)
+    ap.add_argument("--skip-dead-uncond", type=int, default=1,
+                    help="skip the unconditional forward on steps whose guidance scale is exactly 0.0 (bit-identical; FLOPs still "
+                         "counted as the reference executes them)")
+    ap.add_argument("--cpu-batch", type=int, default=4)
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

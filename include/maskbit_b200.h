@@ -141,6 +141,28 @@ int mb_sample(mb_handle* h, const mb_sample_args* a, mb_stream stream);
 /* Number of kernels the library has launched on this handle since creation (bench.py "gpu_launches"). */
 int64_t mb_launch_count(mb_handle* h);
 
+/* Per-kernel-class timing with CUDA events recorded on the launch stream around every launch of the class
+ * (bench.py's live roofline measurement).  mb_profile_enable(h, 1) starts a fresh collection;
+ * mb_profile_read synchronises the device, writes the summed milliseconds and launch counts per class into
+ * ms[MB_PROF_NUM_KINDS] / counts[MB_PROF_NUM_KINDS] and resets the collection. */
+enum mb_prof_kind {
+    MB_PROF_EMBED = 0,      /* bit unpack + input_proj + cls/pos + first LayerNorm */
+    MB_PROF_GEMM_QKV = 1,   /* [M,1024] x [3072,1024]^T */
+    MB_PROF_ATTENTION = 2,
+    MB_PROF_GEMM_OUT = 3,   /* [M,1024] x [1024,1024]^T + residual */
+    MB_PROF_LAYERNORM = 4,
+    MB_PROF_GEMM_UP = 5,    /* [M,1024] x [4096,1024]^T + GELU */
+    MB_PROF_GEMM_DOWN = 6,  /* [M,4096] x [1024,4096]^T + residual */
+    MB_PROF_GEMM_HEAD = 7,  /* last_layer + prediction_layer */
+    MB_PROF_SELECT = 8,
+    MB_PROF_DEC_CONV = 9,   /* decoder 3x3 / 1x1 implicit-GEMM convs */
+    MB_PROF_DEC_GN = 10,    /* GroupNorm statistics */
+    MB_PROF_DEC_IO = 11,    /* conv_in (token unpack) + conv_out */
+    MB_PROF_NUM_KINDS = 12
+};
+int mb_profile_enable(mb_handle* h, int on);
+int mb_profile_read(mb_handle* h, double* ms, int64_t* counts, int n_kinds);
+
 /* ---- unit-test hooks on the individual kernels (device pointers, bf16 = uint16 storage) ---- */
 /* out = epilogue(A[M,K] W[N,K]^T + bias); epi: 0 bias->bf16, 1 bias+gelu->bf16, 2 bias+residual->f32,
  * 3 bias->f32 with class-row drop (seq_in/seq_out), 4 bias+gelu->f32 */

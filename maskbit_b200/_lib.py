@@ -56,10 +56,15 @@ SYMBOLS = {
     "mb_postprocess_u8": (_I, [_P, _P, _I, _P, _P]),
     "mb_sample": (_I, [_P, ctypes.POINTER(MBSampleArgs), _P]),
     "mb_launch_count": (ctypes.c_int64, [_P]),
+    "mb_profile_enable": (_I, [_P, _I]),
+    "mb_profile_read": (_I, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64), _I]),
     "mb_test_gemm": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "mb_test_attention": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "mb_test_layernorm": (_I, [_P, _P, _P, _F, _P, _I, _I, _P]),
 }
+
+PROF_KINDS = ["embed_ln", "gemm_qkv", "attention", "gemm_out", "layernorm", "gemm_up", "gemm_down", "gemm_head", "select",
+              "dec_conv", "dec_groupnorm", "dec_io"]
 
 _lib = None
 

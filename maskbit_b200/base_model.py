@@ -188,3 +188,15 @@ class EngineModel:
 
     def launch_count(self):
         return int(_lib.lib().mb_launch_count(self._handle)) if self._handle is not None else 0
+
+    def profile_enable(self, on=True):
+        """Start (or stop) per-kernel-class CUDA-event timing on this model's handle (mb_profile_enable)."""
+        _lib.check(_lib.lib().mb_profile_enable(self._engine(), int(bool(on))))
+
+    def profile_read(self):
+        """{kernel class: (milliseconds, launches)} since the last read; synchronises the device."""
+        n = len(_lib.PROF_KINDS)
+        ms = (ctypes.c_double * n)()
+        cnt = (ctypes.c_int64 * n)()
+        _lib.check(_lib.lib().mb_profile_read(self._engine(), ms, cnt, n))
+        return {k: (ms[i], int(cnt[i])) for i, k in enumerate(_lib.PROF_KINDS) if cnt[i]}

@@ -171,6 +171,28 @@ struct mb_handle {
     int dec_cap = 0;
     float *dx = nullptr, *dt1 = nullptr, *dt2 = nullptr, *gn_scale = nullptr, *gn_shift = nullptr;
     double2* gn_partial = nullptr;
+    // per-kernel-class CUDA-event timing (mb_profile_*): pairs of events recorded around launches on the launch stream
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    std::vector<int> ev_kind;   // kind of pair i (events 2i, 2i+1)
+};
+
+// RAII scope: records an event pair around the launches issued inside it when profiling is on
+struct ProfScope {
+    mb_handle* h; cudaStream_t st; size_t idx; bool on;
+    ProfScope(mb_handle* h_, int kind, cudaStream_t st_) : h(h_), st(st_), idx(0), on(h_ && h_->profiling) {
+        if (!on) return;
+        if (h->ev_used + 2 > h->ev_pool.size()) {
+            const size_t n = h->ev_pool.size();
+            h->ev_pool.resize(n + 4096);
+            for (size_t i = n; i < h->ev_pool.size(); ++i) cudaEventCreate(&h->ev_pool[i]);
+        }
+        idx = h->ev_used; h->ev_used += 2;
+        h->ev_kind.push_back(kind);
+        cudaEventRecord(h->ev_pool[idx], st);
+    }
+    ~ProfScope() { if (on) cudaEventRecord(h->ev_pool[idx + 1], st); }
 };
 
 template <typename T>
@@ -232,10 +254,30 @@ extern "C" void mb_destroy(mb_handle* h) {
     for (int m = 0; m < 2; ++m) for (auto& kv : h->staged[m]) cudaFree(kv.second.ptr);
     for (void* p : h->allocs) cudaFree(p);
     free_ws(h); free_sample_ws(h); free_dec_ws(h);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
 }
 
 extern "C" int64_t mb_launch_count(mb_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int mb_profile_enable(mb_handle* h, int on) {
+    if (!h) return fail(MB_ERR_INVALID, "mb_profile_enable: null handle");
+    h->profiling = on != 0;
+    h->ev_used = 0; h->ev_kind.clear();
+    return 0;
+}
+extern "C" int mb_profile_read(mb_handle* h, double* ms, int64_t* counts, int n_kinds) {
+    if (!h || !ms || !counts || n_kinds < MB_PROF_NUM_KINDS) return fail(MB_ERR_INVALID, "mb_profile_read: bad argument");
+    CU_TRY(cudaDeviceSynchronize());
+    for (int k = 0; k < n_kinds; ++k) { ms[k] = 0.0; counts[k] = 0; }
+    for (size_t i = 0; i < h->ev_kind.size(); ++i) {
+        float t = 0.f;
+        CU_TRY(cudaEventElapsedTime(&t, h->ev_pool[2 * i], h->ev_pool[2 * i + 1]));
+        ms[h->ev_kind[i]] += t; counts[h->ev_kind[i]]++;
+    }
+    h->ev_used = 0; h->ev_kind.clear();
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------ checkpoint loading
 extern "C" int mb_set_tensor(mb_handle* h, int model, const char* name, const float* data, const int64_t* shape, int ndim,
@@ -467,8 +509,9 @@ static int launch_gemm(mb_handle* h, const CUtensorMap& ta, const CUtensorMap& t
     if (BN == 64) return launch_gemm_bn<64>(h, ta, tb, p, epi, num_sms, st);
     return fail(MB_ERR_INVALID, "bad BN %d", BN);
 }
-static int run_linear(mb_handle* h, const CUtensorMap& ta, const Linear& L, int M, int epi, const __nv_bfloat16* residual,
+static int run_linear(mb_handle* h, int kind, const CUtensorMap& ta, const Linear& L, int M, int epi, const __nv_bfloat16* residual,
                       void* out, int ldo, cudaStream_t st, int seq_in = 0, int seq_out = 0) {
+    ProfScope prof(h, kind, st);
     GemmParams p;
     p.M = M; p.N = L.N; p.K = L.K; p.bias = L.b; p.residual = residual; p.ldr = L.N; p.out = out; p.ldo = ldo;
     p.seq_in = seq_in; p.seq_out = seq_out;
@@ -508,28 +551,33 @@ static int forward_impl(mb_handle* h, const int64_t* tokens, int n_token_rows, c
     const float eps = 1e-12f;
     const int rows_per_blk = 8;
     const unsigned ln_grid = (unsigned)((M + rows_per_blk - 1) / rows_per_blk);
+    { ProfScope prof(h, MB_PROF_EMBED, st);
     embed_ln_kernel<D><<<ln_grid, 256, 0, st>>>(tokens, n_token_rows, labels, n_label_rows, drop, n_seq, c.seq_len, c.codebook_splits,
                                                  h->eff_bits, c.nclass, h->w_in_t, h->b_in, h->class_emb, h->pos, h->ln_first.g,
-                                                 h->ln_first.b, eps, h->x);
+                                                 h->ln_first.b, eps, h->x); }
     CU_TRY(cudaGetLastError()); h->launches++;
     const float sl2 = 1.4426950408889634f / sqrtf((float)ATT_HD);
     for (int l = 0; l < c.depth; ++l) {
         const Layer& L = h->layers[l];
-        MB_TRY(run_linear(h, h->tm_x, L.qkv, M, EPI_BIAS_BF16, nullptr, h->qkv, 3 * D, st));
-        attention_kernel<<<n_seq * c.heads, ATT_THREADS, 2 * ATT_MAXS * ATT_LDS * 2, st>>>(h->qkv, h->att, h->S, D, c.heads, sl2);
+        MB_TRY(run_linear(h, MB_PROF_GEMM_QKV, h->tm_x, L.qkv, M, EPI_BIAS_BF16, nullptr, h->qkv, 3 * D, st));
+        { ProfScope prof(h, MB_PROF_ATTENTION, st);
+        attention_kernel<<<n_seq * c.heads, ATT_THREADS, 2 * ATT_MAXS * ATT_LDS * 2, st>>>(h->qkv, h->att, h->S, D, c.heads, sl2); }
         CU_TRY(cudaGetLastError()); h->launches++;
-        MB_TRY(run_linear(h, h->tm_att, L.out, M, EPI_BIAS_RES_F32, h->x, h->pre, D, st));
-        layernorm_kernel<D><<<ln_grid, 256, 0, st>>>(h->pre, L.ln1.g, L.ln1.b, eps, h->x, M);
+        MB_TRY(run_linear(h, MB_PROF_GEMM_OUT, h->tm_att, L.out, M, EPI_BIAS_RES_F32, h->x, h->pre, D, st));
+        { ProfScope prof(h, MB_PROF_LAYERNORM, st);
+        layernorm_kernel<D><<<ln_grid, 256, 0, st>>>(h->pre, L.ln1.g, L.ln1.b, eps, h->x, M); }
         CU_TRY(cudaGetLastError()); h->launches++;
-        MB_TRY(run_linear(h, h->tm_x, L.up, M, EPI_BIAS_GELU_BF16, nullptr, h->hmid, c.mlp_dim, st));
-        MB_TRY(run_linear(h, h->tm_hmid, L.down, M, EPI_BIAS_RES_F32, h->x, h->pre, D, st));
-        layernorm_kernel<D><<<ln_grid, 256, 0, st>>>(h->pre, L.ln2.g, L.ln2.b, eps, h->x, M);
+        MB_TRY(run_linear(h, MB_PROF_GEMM_UP, h->tm_x, L.up, M, EPI_BIAS_GELU_BF16, nullptr, h->hmid, c.mlp_dim, st));
+        MB_TRY(run_linear(h, MB_PROF_GEMM_DOWN, h->tm_hmid, L.down, M, EPI_BIAS_RES_F32, h->x, h->pre, D, st));
+        { ProfScope prof(h, MB_PROF_LAYERNORM, st);
+        layernorm_kernel<D><<<ln_grid, 256, 0, st>>>(h->pre, L.ln2.g, L.ln2.b, eps, h->x, M); }
         CU_TRY(cudaGetLastError()); h->launches++;
     }
-    MB_TRY(run_linear(h, h->tm_x, h->head, M, 4 /*bias+gelu -> f32*/, nullptr, h->pre, D, st));
-    layernorm_kernel<D><<<ln_grid, 256, 0, st>>>(h->pre, h->ln_head.g, h->ln_head.b, eps, h->att, M);
+    MB_TRY(run_linear(h, MB_PROF_GEMM_HEAD, h->tm_x, h->head, M, 4 /*bias+gelu -> f32*/, nullptr, h->pre, D, st));
+    { ProfScope prof(h, MB_PROF_LAYERNORM, st);
+    layernorm_kernel<D><<<ln_grid, 256, 0, st>>>(h->pre, h->ln_head.g, h->ln_head.b, eps, h->att, M); }
     CU_TRY(cudaGetLastError()); h->launches++;
-    MB_TRY(run_linear(h, h->tm_att, h->pred, M, EPI_BIAS_F32_SEQ, nullptr, logits, h->pred.N, st, h->S, c.seq_len));
+    MB_TRY(run_linear(h, MB_PROF_GEMM_HEAD, h->tm_att, h->pred, M, EPI_BIAS_F32_SEQ, nullptr, logits, h->pred.N, st, h->S, c.seq_len));
     return 0;
 }
 
@@ -552,6 +600,7 @@ static int select_impl(mb_handle* h, const mb_select_args* a, cudaStream_t st) {
     if (a->B <= 0 || slots <= 0 || slots > 4096) return fail(MB_ERR_INVALID, "select: B=%d slots=%d", a->B, slots);
     if (a->tokens_in == a->tokens_out) return fail(MB_ERR_INVALID, "select: tokens_in and tokens_out must be distinct buffers");
     const size_t smem = ((slots * 4 + 15) & ~15) + (size_t)slots * 8;
+    ProfScope prof(h, MB_PROF_SELECT, st);
     switch (a->V) {
         case 32: select_step_kernel<1><<<a->B, 512, smem, st>>>(p); break;
         case 64: select_step_kernel<2><<<a->B, 512, smem, st>>>(p); break;
@@ -606,6 +655,7 @@ static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 static int run_gn(mb_handle* h, const float* x, const GNW& g, int nb, int R, cudaStream_t st) {
     const int HW = R * R;
     int chunks = HW / 1024; if (chunks < 1) chunks = 1; if (chunks > 64) chunks = 64;
+    ProfScope prof(h, MB_PROF_DEC_GN, st);
     gn_partial_kernel<<<dim3(chunks, nb), 256, 0, st>>>(x, h->gn_partial, HW, g.C, chunks);
     CU_TRY(cudaGetLastError()); h->launches++;
     gn_finalize_kernel<<<nb, 256, 0, st>>>(h->gn_partial, g.g, g.b, h->gn_scale, h->gn_shift, HW, g.C, chunks, 1e-6f);
@@ -621,6 +671,7 @@ static int run_conv(mb_handle* h, const float* in, float* out, const ConvW& w, i
     if ((1 << p.logW) != R) return fail(MB_ERR_INVALID, "decoder resolution %d is not a power of two", R);
     const long long npix = (long long)nb * R * R;
     dim3 grid((unsigned)((npix + CV_BM - 1) / CV_BM), w.cout / CV_BN);
+    ProfScope prof(h, MB_PROF_DEC_CONV, st);
     conv_igemm_kernel<<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(p);
     CU_TRY(cudaGetLastError()); h->launches++;
     return 0;
@@ -650,7 +701,8 @@ static int decode_impl(mb_handle* h, const int64_t* tokens, int B, float* images
         float *X = h->dx, *T1 = h->dt1, *T2 = h->dt2;
         int R = P;
         const long long total = (long long)nb * P * P * h->dec_c0;
-        conv_in_tokens_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tokens + (size_t)b0 * c.seq_len, h->cin_w, h->cin_b, X, nb, P, h->bits, h->dec_c0);
+        { ProfScope prof(h, MB_PROF_DEC_IO, st);
+        conv_in_tokens_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tokens + (size_t)b0 * c.seq_len, h->cin_w, h->cin_b, X, nb, P, h->bits, h->dec_c0); }
         CU_TRY(cudaGetLastError()); h->launches++;
         for (auto& rb : h->mid) MB_TRY(run_block(h, rb, X, T1, T2, nb, R, st));
         for (auto& stg : h->ups) {
@@ -663,7 +715,8 @@ static int decode_impl(mb_handle* h, const int64_t* tokens, int B, float* images
         }
         MB_TRY(run_gn(h, X, h->norm_out, nb, R, st));
         dim3 grid((R + CO_T - 1) / CO_T, (R + CO_T - 1) / CO_T, nb);
-        conv_out_kernel<<<grid, 256, 0, st>>>(X, h->gn_scale, h->gn_shift, h->cout_w, h->cout_b, images + (size_t)b0 * 3 * R * R, R, R, h->dec_cl);
+        { ProfScope prof(h, MB_PROF_DEC_IO, st);
+        conv_out_kernel<<<grid, 256, 0, st>>>(X, h->gn_scale, h->gn_shift, h->cout_w, h->cout_b, images + (size_t)b0 * 3 * R * R, R, R, h->dec_cl); }
         CU_TRY(cudaGetLastError()); h->launches++;
     }
     return 0;

@@ -1,0 +1,387 @@
+"""GPU parity tests of the sampling hot path through the reference-facing API (maskbit_b200.LFQBert / ConvVQModel /
+sample -> C ABI), against the golden fixtures recorded from the reference itself (tests/golden/make_golden.py) and
+against the oracle (oracle/, CPU) on seeded inputs.
+
+Parity stages (SURVEY.md 7 hard part a):
+  P1 select path bit-exact given identical logits + noise + schedule      test_select_*
+  P2 generator logits within tolerance of the fp32 reference              test_forward_*
+  P3 decoded pixels within 1e-3 abs of the fp32 reference                 test_decode_*
+  P4 teacher-forced chain over the reference's recorded steps             test_teacher_forced_chain
+  P5 free-running sampler: structural properties at full size             test_sample_*
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from maskbit_b200 import ConvVQModel, LFQBert, _lib, load_config, sample, sampler_kwargs
+from maskbit_b200.masking import step_tables
+from oracle import maskbit_oracle as O
+from oracle import select_oracle as SO
+
+pytestmark = pytest.mark.gpu
+
+# bf16 GEMM operands / bf16 residual stream with fp32 accumulation, LayerNorm and softmax, vs the fp32 reference:
+# the reference's own bf16-autocast run differs from its fp32 run by 3.0e-2 max / 5.4e-3 mean.
+LOGIT_MAX_ABS = 6e-2
+LOGIT_MEAN_ABS = 1e-2
+PIXEL_MAX_ABS = 1e-3   # BASELINE.json north_star: decoded pixels within 1e-3 abs fp32
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+_MODELS = {}
+
+
+def models(bits=12):
+    if bits not in _MODELS:
+        cfg = load_config(f"maskbit_generator_{bits}bit")
+        kw = sampler_kwargs(cfg)
+        mlm = cfg.model.mlm_model
+        tok = ConvVQModel(cfg.model.vq_model, legacy=False).to("cuda")
+        gen = LFQBert(img_size=256, hidden_dim=mlm.hidden_dim, codebook_size=cfg.model.vq_model.codebook_size,
+                      codebook_splits=mlm.codebook_splits, depth=mlm.depth, heads=mlm.heads, mlp_dim=mlm.mlp_dim,
+                      dropout=mlm.dropout, use_prenorm=mlm.use_prenorm, input_stride=16).to("cuda")
+        _MODELS[bits] = (cfg, kw, tok, gen)
+    return _MODELS[bits]
+
+
+def select_step(gen, lc, lu, q, g, tokens_in, *, scale, temperature, rt, omp, mask_len, step=0, seed=0):
+    """One mb_select_step call; returns (predicted, tokens_out)."""
+    B, n, m = tokens_in.shape
+    a = _lib.MBSelectArgs()
+    pred = torch.empty_like(tokens_in)
+    out = torch.empty_like(tokens_in)
+    a.logits_c, a.logits_u = lc.data_ptr(), (lu.data_ptr() if lu is not None else None)
+    a.q, a.gumbel = (q.data_ptr() if q is not None else None), (g.data_ptr() if g is not None else None)
+    a.tokens_in, a.predicted, a.tokens_out = tokens_in.data_ptr(), pred.data_ptr(), out.data_ptr()
+    a.scale, a.temperature, a.randomize_temperature, a.one_minus_progress, a.mask_len = scale, temperature, rt, omp, mask_len
+    a.B, a.n, a.splits, a.V, a.seq_stride = B, n, m, lc.shape[-1], lc.shape[1]
+    a.mask_token, a.seed, a.step = gen.mask_token, seed, step
+    _lib.check(_lib.lib().mb_select_step(gen._engine(), ctypes.byref(a), _lib.current_stream()))
+    torch.cuda.synchronize()
+    return pred, out
+
+
+# ------------------------------------------------------------------------------------------------ P2 forward
+@pytest.mark.parametrize("bits", [12, 14])
+def test_forward_matches_reference_golden(bits, golden_dir):
+    g = np.load(os.path.join(golden_dir, f"forward_{bits}bit.npz"))
+    _, _, _, gen = models(bits)
+    tok = torch.from_numpy(g["tokens"].astype(np.int64)).cuda()
+    labels = torch.from_numpy(g["labels"]).cuda()
+    labels_before = labels.clone()
+    logits = gen(tok, labels, torch.from_numpy(g["drop"]).cuda())
+    ref = torch.from_numpy(g["logits"]).cuda()
+    assert logits.shape == ref.shape and logits.dtype == torch.float32
+    assert torch.equal(labels, labels_before)           # the caller's labels are not mutated (cf. bert.py:484)
+    d = (logits - ref).abs()
+    print(f"forward {bits}bit: max abs {d.max().item():.4e} mean abs {d.mean().item():.4e} (logit range {ref.abs().max().item():.2f})")
+    assert d.max().item() <= LOGIT_MAX_ABS
+    assert d.mean().item() <= LOGIT_MEAN_ABS
+    # conditional and unconditional halves must differ (label / drop handling)
+    n = tok.shape[0] // 2
+    assert (logits[:n] - logits[n:]).abs().max().item() > 1e-3
+
+
+def test_forward_drop_none_and_batch_invariance(golden_dir):
+    """drop_label_mask=None drops every label (the reference quirk `cls_token[None] = 1000`, bert.py:482-484), and a
+    sequence's logits do not depend on what else is in the batch (bit-exact: tiles never mix sequences' rows)."""
+    g = np.load(os.path.join(golden_dir, "forward_12bit.npz"))
+    _, _, _, gen = models(12)
+    tok = torch.from_numpy(g["tokens"].astype(np.int64)).cuda()
+    labels = torch.from_numpy(g["labels"]).cuda()
+    all_drop = gen(tok, labels, torch.ones(tok.shape[0], dtype=torch.bool, device="cuda"))
+    none = gen(tok, labels, None)
+    assert torch.equal(all_drop, none)
+    one = gen(tok[1:2], labels[1:2], torch.ones(1, dtype=torch.bool, device="cuda"))
+    assert torch.equal(one[0], all_drop[1])
+
+
+def test_forward_rejects_bad_input():
+    _, _, _, gen = models(12)
+    with pytest.raises(ValueError):
+        gen(torch.zeros((2, 255, 2), dtype=torch.int64, device="cuda"), torch.zeros(2, dtype=torch.int64, device="cuda"))
+    with pytest.raises(NotImplementedError):
+        gen(torch.zeros((1, 256, 2), dtype=torch.int64, device="cuda"), torch.zeros(1, dtype=torch.int64, device="cuda"),
+            None, return_attn=True)
+
+
+# ------------------------------------------------------------------------------------------------ P1 select
+def test_select_matches_reference_trace(golden_dir):
+    """The reference's recorded per-step logits + replayed RNG draws -> its per-step predicted tokens, bit-exact,
+    and the re-masked state equal to the C oracle's at every step."""
+    g = np.load(os.path.join(golden_dir, "select_12bit.npz"))
+    _, kw, _, gen = models(12)
+    steps, B = g["tokens"].shape[0], g["tokens"].shape[1]
+    scale, temp, omp, mask_len = step_tables(steps, 512, softmax_temperature=kw["softmax_temperature"],
+                                             mask_schedule_strategy=kw["mask_schedule_strategy"],
+                                             guidance_scale=kw["guidance_scale"], guidance_annealing=kw["guidance_annealing"],
+                                             scale_pow=kw["scale_pow"], use_sampling_annealing=kw["use_sampling_annealing"])
+    masked = torch.full((B, 256, 2), kw["mask_token"], dtype=torch.int64, device="cuda")
+    masked_c = masked.cpu().numpy().copy()
+    for i in range(steps):
+        logits = torch.from_numpy(g["logits"][i]).cuda()
+        lc, lu = logits[:B].contiguous(), logits[B:].contiguous()
+        q, gum = torch.from_numpy(g["q"][i]).cuda(), torch.from_numpy(g["g"][i]).cuda()
+        pred, masked = select_step(gen, lc, lu, q, gum, masked, scale=scale[i], temperature=temp[i],
+                                   rt=kw["randomize_temperature"], omp=omp[i], mask_len=mask_len[i], step=i)
+        assert np.array_equal(pred.cpu().numpy(), g["tokens"][i].astype(np.int64)), f"predicted tokens differ at step {i}"
+        _, masked_c, k = SO.select_step(lc.cpu().numpy(), lu.cpu().numpy(), scale[i], temp[i], g["q"][i], g["g"][i],
+                                        kw["randomize_temperature"], omp[i], mask_len[i], masked_c, kw["mask_token"])
+        assert np.array_equal(masked.cpu().numpy(), masked_c), f"re-masked tokens differ at step {i}"
+
+
+@pytest.mark.parametrize("V,B,guided,temperature", [(64, 16, True, 1.0), (128, 8, True, 0.9), (64, 8, False, 1.0),
+                                                     (32, 4, True, 1.3), (256, 3, True, 1.0), (512, 2, False, 0.7)])
+def test_select_random_vs_c_oracle(V, B, guided, temperature):
+    """Seeded random logits / noise / partially decoded state, every per-group vocabulary the shipped configs use
+    (10..18 bit): CUDA select == plain-C oracle, bit for bit (predicted tokens and re-masked state)."""
+    _, kw, _, gen = models(12)
+    gcpu = torch.Generator().manual_seed(V * 131 + B)
+    n, m = 256, 2
+    lc = torch.randn((B, n, m, V), generator=gcpu) * 3
+    lu = torch.randn((B, n, m, V), generator=gcpu) * 3 if guided else None
+    q = torch.empty((B * n * m, V)).exponential_(1, generator=gcpu)
+    gum = -torch.log(-torch.log(torch.rand((B, n, m), generator=gcpu).clamp_min(1e-20)))
+    mask_token = V
+    tok = torch.randint(0, V, (B, n, m), generator=gcpu)
+    # every sample has the same number of masked slots (as in the sampler), at different positions
+    for b in range(B):
+        perm = torch.randperm(n * m, generator=gcpu)[:300]
+        tok[b].view(-1)[perm] = mask_token
+    for mask_len, omp in [(211.0, 0.4), (0.0, 0.0), (600.0, 0.9)]:
+        a = _lib.MBSelectArgs()
+        tin = tok.cuda()
+        pred = torch.empty_like(tin)
+        out = torch.empty_like(tin)
+        lc_d, lu_d, q_d, g_d = lc.cuda(), (lu.cuda() if guided else None), q.cuda(), gum.cuda()
+        a.logits_c, a.logits_u, a.q, a.gumbel = lc_d.data_ptr(), (lu_d.data_ptr() if guided else None), q_d.data_ptr(), g_d.data_ptr()
+        a.tokens_in, a.predicted, a.tokens_out = tin.data_ptr(), pred.data_ptr(), out.data_ptr()
+        a.scale, a.temperature, a.randomize_temperature, a.one_minus_progress, a.mask_len = 2.3, temperature, 8.2, omp, mask_len
+        a.B, a.n, a.splits, a.V, a.seq_stride, a.mask_token, a.seed, a.step = B, n, m, V, n, mask_token, 0, 0
+        _lib.check(_lib.lib().mb_select_step(gen._engine(), ctypes.byref(a), _lib.current_stream()))
+        torch.cuda.synchronize()
+        pred_c, out_c, _ = SO.select_step(lc.numpy(), lu.numpy() if guided else None, 2.3, temperature, q.numpy(), gum.numpy(),
+                                          8.2, omp, mask_len, tok.numpy(), mask_token)
+        assert np.array_equal(pred.cpu().numpy(), pred_c)
+        assert np.array_equal(out.cpu().numpy(), out_c)
+        # already-decoded slots are kept (sampling.py:111) and never re-masked (confidence +inf, sampling.py:115)
+        keep = tok != mask_token
+        assert torch.equal(out.cpu()[keep], tok[keep])
+
+
+def test_select_rejects_aliasing_and_bad_vocab():
+    _, _, _, gen = models(12)
+    t = torch.zeros((1, 256, 2), dtype=torch.int64, device="cuda")
+    lc = torch.zeros((1, 256, 2, 64), device="cuda")
+    a = _lib.MBSelectArgs()
+    a.logits_c, a.tokens_in, a.predicted, a.tokens_out = lc.data_ptr(), t.data_ptr(), t.data_ptr(), t.data_ptr()
+    a.B, a.n, a.splits, a.V, a.seq_stride, a.temperature = 1, 256, 2, 64, 256, 1.0
+    assert _lib.lib().mb_select_step(gen._engine(), ctypes.byref(a), _lib.current_stream()) == -1
+    t2 = torch.zeros_like(t)
+    a.tokens_out, a.V = t2.data_ptr(), 48
+    assert _lib.lib().mb_select_step(gen._engine(), ctypes.byref(a), _lib.current_stream()) == -1
+
+
+# ------------------------------------------------------------------------------------------------ P3 decoder
+def test_decode_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "decode_12bit.npz"))
+    _, _, tokenizer, _ = models(12)
+    tokens = torch.from_numpy(g["tokens"].astype(np.int64)).cuda()
+    img = tokenizer.decode_tokens(tokens)
+    assert img.shape == (2, 3, 256, 256) and img.dtype == torch.float32
+    d0 = (img[0].cpu() - torch.from_numpy(g["image0"])).abs().max().item()
+    ds = (img[:, :, ::4, ::4].cpu() - torch.from_numpy(g["image_sub"])).abs().max().item()
+    print(f"decode: max abs pixel error {max(d0, ds):.3e} (pixel range {float(g['image0'].min()):.2f}..{float(g['image0'].max()):.2f})")
+    assert d0 <= PIXEL_MAX_ABS and ds <= PIXEL_MAX_ABS
+    # any-int / float token dtypes are accepted like the reference (`.long()`, lookup_free.py:108)
+    assert torch.equal(tokenizer.decode_tokens(tokens.float()), img)
+    assert torch.equal(tokenizer.decode_tokens(tokens.int()), img)
+
+
+def test_decode_batch_chunking_and_latents():
+    """B larger than the decoder's internal chunk: every image equals its single-image decode; decode(z) == decode_tokens."""
+    _, _, tokenizer, _ = models(12)
+    g = torch.Generator().manual_seed(5)
+    tokens = torch.randint(0, 4096, (35, 256), generator=g).cuda()
+    img = tokenizer.decode_tokens(tokens)
+    for b in (0, 31, 32, 34):
+        assert torch.equal(tokenizer.decode_tokens(tokens[b:b + 1])[0], img[b])
+    z = O.indices_to_bits(tokens[:2].cpu(), 12).reshape(2, 16, 16, 12).permute(0, 3, 1, 2).contiguous()
+    assert torch.equal(tokenizer.decode(z.cuda()), img[:2])
+    assert tokenizer.decode_tokens(tokens[:0]).shape == (0, 3, 256, 256)   # empty batch
+
+
+def test_postprocess_uint8():
+    _, _, tokenizer, _ = models(12)
+    g = torch.Generator().manual_seed(6)
+    img = (torch.rand((3, 3, 256, 256), generator=g) * 1.6 - 0.3).cuda()
+    ref = (torch.clamp(img, 0.0, 1.0) * 255.0).permute(0, 2, 3, 1).to(torch.uint8)    # eval_maskbit.py:134-135
+    assert torch.equal(tokenizer.postprocess_uint8(img), ref)
+
+
+# ------------------------------------------------------------------------------------------------ P4 teacher forcing
+def test_teacher_forced_chain(golden_dir):
+    """At every recorded step of the reference's own sample() run (B=2, 4 steps): feed the reference's step input
+    tokens to the CUDA forward -> logits within tolerance of the reference's recorded logits; feed the reference's
+    logits to the CUDA select -> the reference's tokens (P1).  Also report how many token choices survive when the
+    CUDA logits replace the reference's (informative: argmax(p/q) is discontinuous)."""
+    g = np.load(os.path.join(golden_dir, "select_12bit.npz"))
+    _, kw, _, gen = models(12)
+    steps, B = g["tokens"].shape[0], g["tokens"].shape[1]
+    scale, temp, omp, mask_len = step_tables(steps, 512, softmax_temperature=kw["softmax_temperature"],
+                                             mask_schedule_strategy=kw["mask_schedule_strategy"],
+                                             guidance_scale=kw["guidance_scale"], guidance_annealing=kw["guidance_annealing"],
+                                             scale_pow=kw["scale_pow"], use_sampling_annealing=kw["use_sampling_annealing"])
+    labels = torch.from_numpy(g["labels"]).cuda()
+    masked = torch.full((B, 256, 2), kw["mask_token"], dtype=torch.int64, device="cuda")
+    drop = torch.cat([torch.zeros(B, dtype=torch.bool), torch.ones(B, dtype=torch.bool)]).cuda()
+    for i in range(steps):
+        ref_logits = torch.from_numpy(g["logits"][i]).cuda()
+        logits = gen(torch.cat([masked, masked]), torch.cat([labels, labels]), drop)
+        d = (logits - ref_logits).abs()
+        assert d.max().item() <= LOGIT_MAX_ABS and d.mean().item() <= LOGIT_MEAN_ABS, f"step {i}: {d.max().item()}"
+        q, gum = torch.from_numpy(g["q"][i]).cuda(), torch.from_numpy(g["g"][i]).cuda()
+        args = dict(scale=scale[i], temperature=temp[i], rt=kw["randomize_temperature"], omp=omp[i], mask_len=mask_len[i], step=i)
+        pred_own, _ = select_step(gen, logits[:B].contiguous(), logits[B:].contiguous(), q, gum, masked, **args)
+        pred, masked = select_step(gen, ref_logits[:B].contiguous(), ref_logits[B:].contiguous(), q, gum, masked, **args)
+        ref_tok = torch.from_numpy(g["tokens"][i].astype(np.int64)).cuda()
+        assert torch.equal(pred, ref_tok)
+        agree = (pred_own == ref_tok).float().mean().item()
+        print(f"step {i}: logits max abs {d.max().item():.3e}; token agreement with own logits {agree:.4f}")
+        assert agree >= 0.90
+
+
+# ------------------------------------------------------------------------------------------------ P5 sampler
+def _k_table(steps, kw):
+    _, _, _, mask_len = step_tables(steps, 512, softmax_temperature=1.0, mask_schedule_strategy=kw["mask_schedule_strategy"],
+                                    guidance_scale=kw["guidance_scale"], guidance_annealing=kw["guidance_annealing"],
+                                    scale_pow=kw["scale_pow"], use_sampling_annealing=False)
+    ks, masked = [], 512
+    for ml in mask_len:
+        k = int(min(max(ml, 1.0), masked - 1))
+        ks.append(k)
+        masked = k
+    return ks
+
+
+def test_sample_config1_structure(golden_dir):
+    """BASELINE config #1 (B=4, 8 steps) with the reference's own noise stream: the first step (all tokens masked,
+    identical inputs) agrees with the reference's tokens except where bf16 logits flip an argmax; every step reveals
+    exactly the scheduled number of tokens; pixels are finite and in the decoder's range."""
+    g = np.load(os.path.join(golden_dir, "sample_12bit.npz"))
+    _, kw, tokenizer, gen = models(12)
+    kw = dict(kw, num_steps=8)
+    labels = torch.from_numpy(g["labels"])
+    torch.manual_seed(1234)
+    img, trace = sample(gen, tokenizer, num_samples=4, labels=labels, noise="reference_cpu", **kw)
+    assert img.shape == (4, 3, 256, 256) and len(trace) == 8 and trace[0].shape == (4, 256, 2) and trace[0].dtype == torch.int64
+    assert torch.isfinite(img).all()
+    ref0 = torch.from_numpy(g["tokens"][0].astype(np.int64)).cuda()
+    agree = (trace[0] == ref0).float().mean().item()
+    print(f"config1 step-0 token agreement with the reference: {agree:.4f}")
+    assert agree >= 0.95
+    ks = _k_table(8, kw)
+    for i in range(7):
+        kept = (trace[i + 1] == trace[i]).reshape(4, -1).sum(1)   # tokens fixed after step i stay fixed
+        assert (kept >= 512 - ks[i]).all()
+    assert all(int(t.max()) < 64 and int(t.min()) >= 0 for t in trace)
+    # decode of the last step's tokens == what sample returned (sampling.py:133-135)
+    from maskbit_b200 import combine_factorized_tokens
+    comb = combine_factorized_tokens(trace[-1], 4096, 2)
+    assert torch.equal(tokenizer.decode_tokens(comb), img)
+
+
+def test_sample_matches_stepwise_composition():
+    """mb_sample's device-resident loop == calling LFQBert.forward + mb_select_step per step from Python with the
+    same injected noise (bit-exact), including the unguided branch (guidance_scale == 0, sampling.py:100-101)."""
+    _, kw, tokenizer, gen = models(12)
+    B, steps = 3, 5
+    gcpu = torch.Generator().manual_seed(11)
+    labels = torch.randint(0, 1000, (B,), generator=gcpu)
+    q = torch.empty((steps, B * 512, 64)).exponential_(1, generator=gcpu)
+    gum = -torch.log(-torch.log(torch.rand((steps, B, 256, 2), generator=gcpu).clamp_min(1e-20)))
+    for gs in (kw["guidance_scale"], 0.0):
+        kws = dict(kw, num_steps=steps, guidance_scale=gs)
+        img, trace = sample(gen, tokenizer, num_samples=B, labels=labels, noise=(q, gum), **kws)
+        scale, temp, omp, mask_len = step_tables(steps, 512, softmax_temperature=kw["softmax_temperature"],
+                                                 mask_schedule_strategy=kw["mask_schedule_strategy"], guidance_scale=gs,
+                                                 guidance_annealing=kw["guidance_annealing"], scale_pow=kw["scale_pow"],
+                                                 use_sampling_annealing=False)
+        masked = torch.full((B, 256, 2), kw["mask_token"], dtype=torch.int64, device="cuda")
+        lab = labels.cuda()
+        for i in range(steps):
+            if gs != 0.0:
+                drop = torch.cat([torch.zeros(B, dtype=torch.bool), torch.ones(B, dtype=torch.bool)]).cuda()
+                logits = gen(torch.cat([masked, masked]), torch.cat([lab, lab]), drop)
+                lc, lu = logits[:B].contiguous(), logits[B:].contiguous()
+            else:
+                lc, lu = gen(masked, lab, torch.zeros(B, dtype=torch.bool, device="cuda")), None
+            pred, masked = select_step(gen, lc, lu, q[i].cuda(), gum[i].cuda(), masked, scale=scale[i], temperature=temp[i],
+                                       rt=kw["randomize_temperature"], omp=omp[i], mask_len=mask_len[i], step=i)
+            assert torch.equal(pred, trace[i]), f"gs={gs} step {i}"
+        # skipping the dead unconditional half on zero-scale steps is bit-identical
+        if gs != 0.0:
+            img2, trace2 = sample(gen, tokenizer, num_samples=B, labels=labels, noise=(q, gum), skip_zero_scale_uncond=True, **kws)
+            assert all(torch.equal(a, b) for a, b in zip(trace, trace2)) and torch.equal(img, img2)
+
+
+def test_sample_device_noise_full_size_properties():
+    """BASELINE config #2 size (B=256, 64 steps, device Philox noise): the number of still-masked slots after every
+    step equals the schedule's k for every sample; same seed -> identical tokens; different seed -> different."""
+    _, kw, tokenizer, gen = models(12)
+    B, steps = 256, 64
+    labels = torch.arange(B) % 1000
+    img, trace = sample(gen, tokenizer, num_samples=B, labels=labels, noise="device", seed=7, **dict(kw, num_steps=steps))
+    assert img.shape == (B, 3, 256, 256) and torch.isfinite(img).all()
+    ks = _k_table(steps, kw)
+    for i in range(steps - 1):
+        changed = (trace[i + 1] != trace[i]).reshape(B, -1).sum(1)
+        assert (changed <= ks[i]).all(), f"step {i}: more than k={ks[i]} slots changed"
+    assert all(int(t.max()) < 64 and int(t.min()) >= 0 for t in trace)
+    _, trace_b = sample(gen, tokenizer, num_samples=B, labels=labels, noise="device", seed=7, **dict(kw, num_steps=steps))
+    assert all(torch.equal(a, b) for a, b in zip(trace, trace_b))
+    _, trace_c = sample(gen, tokenizer, num_samples=4, labels=labels[:4], noise="device", seed=8, **dict(kw, num_steps=8))
+    _, trace_d = sample(gen, tokenizer, num_samples=4, labels=labels[:4], noise="device", seed=9, **dict(kw, num_steps=8))
+    assert not torch.equal(trace_c[0], trace_d[0])
+
+
+def test_sample_argument_errors():
+    _, kw, tokenizer, gen = models(12)
+    with pytest.raises(ValueError):
+        sample(gen, tokenizer, num_samples=2, labels=torch.zeros(2, dtype=torch.long), **dict(kw, mask_schedule_strategy="bogus"))
+    with pytest.raises(ValueError):
+        sample(gen, tokenizer, num_samples=2, labels=torch.zeros(2, dtype=torch.long), **dict(kw, guidance_annealing="bogus"))
+    with pytest.raises(ValueError):
+        sample(gen, tokenizer, num_samples=2, labels=torch.zeros(3, dtype=torch.long), **kw)
+    with pytest.raises(ValueError):
+        sample(gen, tokenizer, num_samples=2, labels=torch.zeros(2, dtype=torch.long), **dict(kw, mask_token=1024))
+
+
+def test_strict_checkpoint_loading(tmp_path):
+    """load_pretrained: strict key check, shape check, rename_keys prefix mapping (base_model.py:87-142)."""
+    cfg, kw, _, gen = models(12)
+    sd = gen.state_dict()
+    old = {k.replace("input_proj", "token_emb"): v for k, v in sd.items()}
+    torch.save(old, tmp_path / "pytorch_model.bin")
+    mlm = cfg.model.mlm_model
+    g2 = LFQBert(img_size=256, hidden_dim=mlm.hidden_dim, codebook_size=4096, codebook_splits=2, depth=mlm.depth, heads=mlm.heads,
+                 mlp_dim=mlm.mlp_dim, dropout=0.0, use_prenorm=False, input_stride=16)
+    with pytest.raises(RuntimeError):
+        g2.load_pretrained(str(tmp_path))                                   # token_emb.* unexpected, input_proj.* missing
+    g2.load_pretrained(str(tmp_path), rename_keys={"token_emb": "input_proj"})
+    g2.to("cuda")
+    tok = torch.full((1, 256, 2), 64, dtype=torch.int64, device="cuda")
+    lab = torch.tensor([3], device="cuda")
+    assert torch.equal(g2(tok, lab, None), gen(tok, lab, None))
+    bad = dict(sd)
+    bad["prediction_layer.weight"] = torch.zeros((64, 1024))
+    with pytest.raises(RuntimeError):
+        g2.load_state_dict(bad)
+    with pytest.raises(ValueError):
+        g2.load_pretrained(str(tmp_path / "nope"))
