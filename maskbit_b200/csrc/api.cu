@@ -14,6 +14,7 @@
 
 #include "../../include/maskbit_b200.h"
 #include "attention.cuh"
+#include "attention_tc.cuh"
 #include "decoder.cuh"
 #include "embed_ln.cuh"
 #include "gemm_tcgen05.cuh"
@@ -157,7 +158,7 @@ struct mb_handle {
     int cap_seqs = 0; size_t cap_rows = 0;
     __nv_bfloat16 *x = nullptr, *qkv = nullptr, *att = nullptr, *hmid = nullptr;
     float* pre = nullptr;
-    CUtensorMap tm_x, tm_att, tm_hmid;
+    CUtensorMap tm_x, tm_att, tm_hmid, tm_qkv_big, tm_qkv_row;
     // sampler workspace
     int cap_sample_B = 0;
     int64_t *tok_a = nullptr, *tok_b = nullptr, *pred_buf = nullptr, *combined = nullptr;
@@ -467,6 +468,7 @@ static int init_kernel_attrs() {
     if (done) return 0;
     MB_TRY(set_gemm_attr_bn<64>()); MB_TRY(set_gemm_attr_bn<128>()); MB_TRY(set_gemm_attr_bn<256>());
     CU_TRY(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ATT_MAXS * ATT_LDS * 2));
+    CU_TRY(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_BYTES));
     done = true;
     return 0;
@@ -536,7 +538,28 @@ static int ensure_ws(mb_handle* h, int n_seq) {
     MB_TRY(make_tmap_bf16(&h->tm_x, h->x, rows, D, 128));
     MB_TRY(make_tmap_bf16(&h->tm_att, h->att, rows, D, 128));
     MB_TRY(make_tmap_bf16(&h->tm_hmid, h->hmid, rows, h->cfg.mlp_dim, 128));
+    MB_TRY(make_tmap_bf16(&h->tm_qkv_big, h->qkv, rows, 3 * D, 256));
+    MB_TRY(make_tmap_bf16(&h->tm_qkv_row, h->qkv, rows, 3 * D, 16));
     h->cap_seqs = n_seq; h->cap_rows = rows;
+    return 0;
+}
+
+// softmax(Q K^T / 8) V for every (sequence, head): the persistent tcgen05 kernel for the 257-token grid, the generic
+// mma.sync kernel for any other sequence length
+static int run_attention(mb_handle* h, const CUtensorMap& tm_big, const CUtensorMap& tm_row, const __nv_bfloat16* qkv,
+                         __nv_bfloat16* out, int n_seq, int S, int D, int H, int num_sms, cudaStream_t st) {
+    const float sl2 = 1.4426950408889634f / sqrtf((float)ATT_HD);
+    ProfScope prof(h, MB_PROF_ATTENTION, st);
+    if (S == 257) {
+        AttnTcParams p;
+        p.out = out; p.n_items = n_seq * H; p.H = H; p.D = D; p.sl2 = sl2;
+        const int grid = p.n_items < num_sms ? p.n_items : num_sms;
+        attention_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM_BYTES, st>>>(tm_big, tm_row, p);
+    } else {
+        attention_kernel<<<n_seq * H, ATT_THREADS, 2 * ATT_MAXS * ATT_LDS * 2, st>>>(qkv, out, S, D, H, sl2);
+    }
+    CU_TRY(cudaGetLastError());
+    if (h) h->launches++;
     return 0;
 }
 
@@ -556,13 +579,10 @@ static int forward_impl(mb_handle* h, const int64_t* tokens, int n_token_rows, c
                                                  h->eff_bits, c.nclass, h->w_in_t, h->b_in, h->class_emb, h->pos, h->ln_first.g,
                                                  h->ln_first.b, eps, h->x); }
     CU_TRY(cudaGetLastError()); h->launches++;
-    const float sl2 = 1.4426950408889634f / sqrtf((float)ATT_HD);
     for (int l = 0; l < c.depth; ++l) {
         const Layer& L = h->layers[l];
         MB_TRY(run_linear(h, MB_PROF_GEMM_QKV, h->tm_x, L.qkv, M, EPI_BIAS_BF16, nullptr, h->qkv, 3 * D, st));
-        { ProfScope prof(h, MB_PROF_ATTENTION, st);
-        attention_kernel<<<n_seq * c.heads, ATT_THREADS, 2 * ATT_MAXS * ATT_LDS * 2, st>>>(h->qkv, h->att, h->S, D, c.heads, sl2); }
-        CU_TRY(cudaGetLastError()); h->launches++;
+        MB_TRY(run_attention(h, h->tm_qkv_big, h->tm_qkv_row, h->qkv, h->att, n_seq, h->S, D, c.heads, h->num_sms, st));
         MB_TRY(run_linear(h, MB_PROF_GEMM_OUT, h->tm_att, L.out, M, EPI_BIAS_RES_F32, h->x, h->pre, D, st));
         { ProfScope prof(h, MB_PROF_LAYERNORM, st);
         layernorm_kernel<D><<<ln_grid, 256, 0, st>>>(h->pre, L.ln1.g, L.ln1.b, eps, h->x, M); }
@@ -822,11 +842,11 @@ extern "C" int mb_test_gemm(const uint16_t* A, const uint16_t* W, const float* b
 extern "C" int mb_test_attention(const uint16_t* qkv, uint16_t* out, int n_seq, int S, int D, int H, mb_stream stream) {
     MB_TRY(init_kernel_attrs());
     if (D / H != ATT_HD || S > ATT_MAXS || (S % 64) > 16) return fail(MB_ERR_INVALID, "attention shape unsupported");
-    const float sl2 = 1.4426950408889634f / sqrtf((float)ATT_HD);
-    attention_kernel<<<n_seq * H, ATT_THREADS, 2 * ATT_MAXS * ATT_LDS * 2, (cudaStream_t)stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), S, D, H, sl2);
-    CU_TRY(cudaGetLastError());
-    return 0;
+    CUtensorMap tb, tr;
+    MB_TRY(make_tmap_bf16(&tb, qkv, (uint64_t)n_seq * S, 3 * D, 256));
+    MB_TRY(make_tmap_bf16(&tr, qkv, (uint64_t)n_seq * S, 3 * D, 16));
+    return run_attention(nullptr, tb, tr, reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out),
+                         n_seq, S, D, H, test_num_sms(), (cudaStream_t)stream);
 }
 extern "C" int mb_test_layernorm(const float* in, const float* gamma, const float* beta, float eps, uint16_t* out, int rows, int D,
                                  mb_stream stream) {

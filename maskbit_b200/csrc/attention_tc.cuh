@@ -6,15 +6,18 @@
 //               (row 256 of Q, K, V) into a 2-stage shared-memory ring
 //   warp 1      MMA issuer (one thread): per 128-query tile t:  S_t = Q_t K^T  (tcgen05.mma M128 N256 K64, smem x smem)
 //                                                               O_t = P_t V    (A = P from TMEM, B = V MN-major from smem)
-//   warp 2      class-token query row (q = 256) on CUDA cores: 257 dot products, softmax, 257-term weighted V sum
-//   warp 3      TMEM allocator (512 columns)
+//   warps 2,3   class-token query row (q = 256) on CUDA cores, alternating items: 257 dot products, softmax, 257-term
+//               weighted V sum; warp 3 also allocates TMEM (512 columns)
 //   warps 4-11  softmax: warpgroup t owns query tile t, thread = one query row.  Two passes over S_t in TMEM
-//               (max, then exp2 -> bf16 P written back over S), the class-token KEY (k = 256) handled as a rank-1 side
-//               path (score on CUDA cores, its P*V added in the epilogue), then O_t / l -> bf16 -> global.
-// TMEM per query tile (256 columns): [0,128) P as packed bf16x2 (aliases S columns already consumed), [128,192) O.
+//               (max, then exp2 -> bf16 P written back over S), then (O_t + p256 v256) / l -> bf16 -> global.
+//               The class-token KEY (k = 256) is a rank-1 side path: its score column comes from a 16-wide MMA
+//               (Q_t x K[256..271]^T, column 0 used) issued with P V, its P*V is added in the epilogue.  Row sums l are
+//               also produced by the tensor core (P x ones) so that the exp loop is FFMA2 + MUFU + F2FP only.
+// TMEM per query tile (256 columns): [0,128) P as packed bf16x2 (aliases S columns already consumed), [128,192) O,
+//               [192,208) class-key scores, [208,224) row sums.
 // 257 = 2*128 + 1: tensor tiles cover the 256x256 block exactly; the odd row and column never touch a padded MMA tile.
 //
-// Input  qkv  bf16 [rows, 3*D] through two TMA maps (box 64x256 and box 64x8); head h at columns h*64 of each third
+// Input  qkv  bf16 [rows, 3*D] through two TMA maps (box 64x256 and box 64x16); head h at columns h*64 of each third
 // Output out  bf16 [n_seq*257, D]
 #pragma once
 #include "ptx.cuh"
@@ -23,9 +26,10 @@ namespace mb {
 
 constexpr int ATC_THREADS = 384;
 constexpr int ATC_TILE_BYTES = 256 * 128;             // 256 rows x 64 bf16
-constexpr int ATC_ROW_BYTES = 8 * 128;                // 8-row box holding the class-token row in its first 128 B
+constexpr int ATC_ROW_BYTES = 16 * 128;               // 16-row box holding the class-token row in its first 128 B
 constexpr int ATC_STAGE_BYTES = 3 * ATC_TILE_BYTES + 3 * ATC_ROW_BYTES;
-constexpr int ATC_SMEM_BYTES = 2 * ATC_STAGE_BYTES + 1024 /*align*/ + 2048 /*p_cls + barriers*/;
+constexpr int ATC_ONES_BYTES = 16 * 128;              // B operand of the row-sum MMA: 16 x 64 bf16 ones
+constexpr int ATC_SMEM_BYTES = 2 * ATC_STAGE_BYTES + ATC_ONES_BYTES + 1024 /*align*/ + 2304 /*p_cls*/ + 256 /*barriers*/;
 
 // D[tmem] (+)= A[tmem] * B[smem]
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -66,6 +70,26 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ float fast_exp2(float x) {   // MUFU.EX2; arguments here are <= 0, ftz is harmless
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// packed fp32 pairs (FFMA2 / FMUL2 on sm_100): one issue slot for two lanes' worth of work
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 __device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
@@ -96,8 +120,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
     extern __shared__ uint8_t atc_smem_raw[];
     const uint32_t raw = smem_u32(atc_smem_raw);
     uint8_t* base = atc_smem_raw + ((1024u - (raw & 1023u)) & 1023u);
-    float* p_cls = reinterpret_cast<float*>(base + 2 * ATC_STAGE_BYTES);            // [272] class-row probabilities
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + 2 * ATC_STAGE_BYTES + 1280);
+    uint32_t* ones = reinterpret_cast<uint32_t*>(base + 2 * ATC_STAGE_BYTES);        // 2 KB of bf16 1.0
+    float* p_cls = reinterpret_cast<float*>(base + 2 * ATC_STAGE_BYTES + ATC_ONES_BYTES);   // [2][288] class-row probabilities
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + 2 * ATC_STAGE_BYTES + ATC_ONES_BYTES + 2304);
     uint64_t* full = bars;          // [2] TMA landed
     uint64_t* empty = bars + 2;     // [2] stage consumed (MMA commit + 8 softmax warps + class warp)
     uint64_t* s_full = bars + 4;    // [2] S_t complete in TMEM
@@ -116,6 +141,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
         fence_mbar_init();
     }
     if (warp == 3) tmem_alloc<512>(tmem_slot);
+    for (int i = threadIdx.x; i < ATC_ONES_BYTES / 4; i += ATC_THREADS) ones[i] = 0x3f803f80u;
+    fence_async_proxy();                                    // generic-proxy smem writes -> visible to tcgen05.mma
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -144,6 +171,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
         if (lane == 0) {  // ---------------------------------------------------------------- MMA issuer
             constexpr uint32_t idesc_s = make_idesc(1, 128, 256);
             constexpr uint32_t idesc_o = make_idesc(1, 128, 64) | (1u << 16);   // B (= V) is MN-major
+            constexpr uint32_t idesc_16 = make_idesc(1, 128, 16);
+            const uint64_t ones_desc = make_sdesc_k128(smem0 + 2 * ATC_STAGE_BYTES);
             uint32_t it = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
                 const int st = it & 1; const uint32_t ph = (it >> 1) & 1, ip = it & 1;
@@ -164,40 +193,54 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
                     mbar_wait(&p_full[t], ip);
                     tc_fence_after();
                     const uint64_t b = make_sdesc_mn128(sv);
+                    const uint32_t tr = tmem_base + t * 256;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        umma_f16_ts(tmem_base + t * 256 + 128, tmem_base + t * 256 + 8 * j, b + (uint64_t)(j * 128), idesc_o, j != 0);
+                    for (int j = 0; j < 16; ++j) {
+                        umma_f16_ts(tr + 128, tr + 8 * j, b + (uint64_t)(j * 128), idesc_o, j != 0);      // O += P_j V_j
+                        umma_f16_ts(tr + 208, tr + 8 * j, ones_desc, idesc_16, j != 0);                   // l += P_j 1
+                    }
+                    const uint64_t a = make_sdesc_k128(sq + t * 128 * 128), kc16 = make_sdesc_k128(sq + 3 * ATC_TILE_BYTES + ATC_ROW_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(tr + 192, a + 2 * k, kc16 + 2 * k, idesc_16, k != 0);  // Q_t K[256..]^T
                     umma_commit(&o_full[t]);
                 }
                 umma_commit(&empty[st]);
             }
         }
-    } else if (warp == 2) {  // ------------------------------------------------------------ class-token query row
+    } else if (warp == 2 || warp == 3) {  // -------------------------------------------- class-token query row
+        // warps 2 and 3 alternate work items (each item's class row costs ~2.5k instructions of one warp)
+        float* pc = p_cls + (warp - 2) * 288;
         uint32_t it = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+            if ((it & 1) != (uint32_t)(warp - 2)) continue;
             const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
             const int seq = item / p.H, head = item - seq * p.H;
             const uint32_t sq = smem0 + st * ATC_STAGE_BYTES, sk = sq + ATC_TILE_BYTES, sv = sk + ATC_TILE_BYTES;
             const uint32_t qc = sq + 3 * ATC_TILE_BYTES, kc = qc + ATC_ROW_BYTES, vc = kc + ATC_ROW_BYTES;
             mbar_wait(&full[st], ph);
-            uint4 q[8];
+            float q[64];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) q[c] = lds128(qc + c * 16);
+            for (int c = 0; c < 8; ++c) {
+                const uint4 w = lds128(qc + c * 16);
+                q[8 * c + 0] = bf_lo(w.x); q[8 * c + 1] = bf_hi(w.x); q[8 * c + 2] = bf_lo(w.y); q[8 * c + 3] = bf_hi(w.y);
+                q[8 * c + 4] = bf_lo(w.z); q[8 * c + 5] = bf_hi(w.z); q[8 * c + 6] = bf_lo(w.w); q[8 * c + 7] = bf_hi(w.w);
+            }
+            auto qdot = [&](uint32_t row_addr, int rsw) {
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint4 w = lds128(row_addr + ((c ^ rsw) << 4));
+                    a0 = fmaf(q[8 * c + 0], bf_lo(w.x), a0); a1 = fmaf(q[8 * c + 1], bf_hi(w.x), a1);
+                    a0 = fmaf(q[8 * c + 2], bf_lo(w.y), a0); a1 = fmaf(q[8 * c + 3], bf_hi(w.y), a1);
+                    a0 = fmaf(q[8 * c + 4], bf_lo(w.z), a0); a1 = fmaf(q[8 * c + 5], bf_hi(w.z), a1);
+                    a0 = fmaf(q[8 * c + 6], bf_lo(w.w), a0); a1 = fmaf(q[8 * c + 7], bf_hi(w.w), a1);
+                }
+                return a0 + a1;
+            };
             float sc[9];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int key = lane + 32 * r;
-                float a = 0.f;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) a = dot8(q[c], lds128(sw128(sk, key, c)), a);
-                sc[r] = a;
-            }
-            {
-                float a = 0.f;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) a = dot8(q[c], lds128(kc + c * 16), a);
-                sc[8] = a;                                  // key 256 (same value in every lane)
-            }
+            for (int r = 0; r < 8; ++r) sc[r] = qdot(sk + (lane + 32 * r) * 128, lane & 7);
+            sc[8] = qdot(kc, 0);                            // key 256 (same value in every lane)
             float mx = sc[8];
 #pragma unroll
             for (int r = 0; r < 8; ++r) mx = fmaxf(mx, sc[r]);
@@ -205,34 +248,49 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
             for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             const float ms = mx * p.sl2;
             float sum = 0.f;
-            __syncwarp();                                   // previous item's readers of p_cls are done
+            __syncwarp();                                   // previous readers of pc are done
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                const float e = exp2f(fmaf(sc[r], p.sl2, -ms));
+                const float e = fast_exp2(fmaf(sc[r], p.sl2, -ms));
                 sum += e;
-                p_cls[lane + 32 * r] = e;
+                pc[lane + 32 * r] = e;
             }
 #pragma unroll
             for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            const float e256 = exp2f(fmaf(sc[8], p.sl2, -ms));
+            const float e256 = fast_exp2(fmaf(sc[8], p.sl2, -ms));
             sum += e256;
             __syncwarp();
-            // out[d], d = 2*lane, 2*lane+1
-            float o0 = 0.f, o1 = 0.f;
-            const int ch = lane >> 2, sub = (lane & 3) * 4;
-#pragma unroll 8
-            for (int key = 0; key < 256; ++key) {
-                const float pk = p_cls[key];
-                const uint32_t w = lds32(sw128(sv, key, ch) + sub);
-                o0 = fmaf(pk, bf_lo(w), o0); o1 = fmaf(pk, bf_hi(w), o1);
+            // P V: lane = (key group kg = lane >> 3: keys kg, kg+4, ...; dim chunk dc = lane & 7: dims 8dc..8dc+7)
+            const int kg = lane >> 3, dc = lane & 7;
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll 4
+            for (int i = 0; i < 64; ++i) {
+                const int key = kg + 4 * i;
+                const float pk = pc[key];
+                const uint4 w = lds128(sw128(sv, key, dc));
+                o[0] = fmaf(pk, bf_lo(w.x), o[0]); o[1] = fmaf(pk, bf_hi(w.x), o[1]);
+                o[2] = fmaf(pk, bf_lo(w.y), o[2]); o[3] = fmaf(pk, bf_hi(w.y), o[3]);
+                o[4] = fmaf(pk, bf_lo(w.z), o[4]); o[5] = fmaf(pk, bf_hi(w.z), o[5]);
+                o[6] = fmaf(pk, bf_lo(w.w), o[6]); o[7] = fmaf(pk, bf_hi(w.w), o[7]);
             }
-            {
-                const uint32_t w = lds32(vc + lane * 4);
-                o0 = fmaf(e256, bf_lo(w), o0); o1 = fmaf(e256, bf_hi(w), o1);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                o[j] += __shfl_xor_sync(0xffffffffu, o[j], 8);
+                o[j] += __shfl_xor_sync(0xffffffffu, o[j], 16);
             }
-            const float inv = 1.0f / sum;
-            __nv_bfloat16* orow = p.out + ((size_t)seq * S + 256) * p.D + head * 64;
-            reinterpret_cast<uint32_t*>(orow)[lane] = pack2_bf16(o0 * inv, o1 * inv);
+            if (kg == 0) {
+                const uint4 w = lds128(vc + dc * 16);
+                const float inv = 1.0f / sum;
+                uint4 r;
+                r.x = pack2_bf16(fmaf(e256, bf_lo(w.x), o[0]) * inv, fmaf(e256, bf_hi(w.x), o[1]) * inv);
+                r.y = pack2_bf16(fmaf(e256, bf_lo(w.y), o[2]) * inv, fmaf(e256, bf_hi(w.y), o[3]) * inv);
+                r.z = pack2_bf16(fmaf(e256, bf_lo(w.z), o[4]) * inv, fmaf(e256, bf_hi(w.z), o[5]) * inv);
+                r.w = pack2_bf16(fmaf(e256, bf_lo(w.w), o[6]) * inv, fmaf(e256, bf_hi(w.w), o[7]) * inv);
+                __nv_bfloat16* orow = p.out + ((size_t)seq * S + 256) * p.D + head * 64;
+                reinterpret_cast<uint4*>(orow)[dc] = r;
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[st]);
         }
@@ -244,59 +302,70 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
             const int st = it & 1; const uint32_t ph = (it >> 1) & 1, ip = it & 1;
             const int seq = item / p.H, head = item - seq * p.H;
-            const uint32_t sq = smem0 + st * ATC_STAGE_BYTES;
-            const uint32_t kc = sq + 3 * ATC_TILE_BYTES + ATC_ROW_BYTES, vc = kc + ATC_ROW_BYTES;
-            mbar_wait(&full[st], ph);
-            float s256 = 0.f;                                          // score against the class-token key
-#pragma unroll
-            for (int c = 0; c < 8; ++c) s256 = dot8(lds128(sw128(sq, row, c)), lds128(kc + c * 16), s256);
+            const uint32_t vc = smem0 + st * ATC_STAGE_BYTES + 3 * ATC_TILE_BYTES + 2 * ATC_ROW_BYTES;
             mbar_wait(&s_full[t], ip);
             tc_fence_after();
-            float mx = s256;
-#pragma unroll 1
-            for (int c = 0; c < 8; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(treg + c * 32, v);
-                tmem_ld_wait();
+            float mx = -INFINITY;
+            uint32_t va[32], vb[32];
+            // pass 1: row max over keys 0..255.  The load of chunk c+1 is in flight while chunk c is reduced.
+            tmem_ld_32x32(treg, va);
+            tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-            }
-            const float ms = mx * p.sl2;
-            float sum = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 8; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(treg + c * 32, v);
+            for (int c = 0; c < 8; c += 2) {
+                tmem_ld_32x32(treg + (c + 1) * 32, vb);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(va[j]));
                 tmem_ld_wait();
+                tmem_ld_32x32(treg + ((c + 2) & 7) * 32, va);      // wraps to chunk 0: first chunk of pass 2
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(vb[j]));
+                tmem_ld_wait();
+            }
+            const float nms = -mx * p.sl2;
+            // pass 2: p = exp2(s * sl2 - max * sl2) -> bf16 pairs written over S columns already consumed
+            auto exp_store = [&](const uint32_t (&v)[32], int c) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const float e0 = exp2f(fmaf(__uint_as_float(v[2 * j]), p.sl2, -ms));
-                    const float e1 = exp2f(fmaf(__uint_as_float(v[2 * j + 1]), p.sl2, -ms));
-                    sum += e0 + e1;
-                    pk[j] = pack2_bf16(e0, e1);
+                    float x0, x1;
+                    ffma2(x0, x1, __uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), p.sl2, p.sl2, nms, nms);
+                    pk[j] = pack2_bf16(fast_exp2(x0), fast_exp2(x1));
                 }
-                tmem_st_32x32_x16(treg + c * 16, pk);                  // P over the S columns already consumed
+                tmem_st_32x32_x16(treg + c * 16, pk);
+            };
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+                tmem_ld_32x32(treg + (c + 1) * 32, vb);
+                exp_store(va, c);
+                tmem_ld_wait();
+                if (c + 2 < 8) tmem_ld_32x32(treg + (c + 2) * 32, va);
+                exp_store(vb, c + 1);
+                if (c + 2 < 8) tmem_ld_wait();
             }
-            const float e256 = exp2f(fmaf(s256, p.sl2, -ms));
-            sum += e256;
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[t]);
-            // epilogue: O_t (64 fp32 columns) + e256 * V[256], / sum -> bf16 row
-            const float inv = 1.0f / sum;
+            // epilogue: (O_t + p256 * V[256]) / (l + p256) -> bf16 row
+            mbar_wait(&full[st], ph);                                  // (long complete) makes the TMA-written V[256] row visible
             uint4 vrow[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) vrow[c] = lds128(vc + c * 16);
             mbar_wait(&o_full[t], ip);
             tc_fence_after();
+            tmem_ld_32x32(treg + 192, va);                             // [0] class-key score, [16] row sum
+            tmem_ld_32x32(treg + 128, vb);                             // O columns 0..31
+            tmem_ld_wait();
+            // exponent clamped: if the class key dominates by more than 2^100 the result is V[256] to fp32 precision anyway
+            const float e256 = fast_exp2(fminf(fmaf(__uint_as_float(va[0]), p.sl2, nms), 100.0f));
+            const float inv = 1.0f / (__uint_as_float(va[16]) + e256);
+            const float ei = e256 * inv;
             __nv_bfloat16* orow = p.out + ((size_t)seq * S + row) * p.D + head * 64;
+            tmem_ld_32x32(treg + 160, va);                             // O columns 32..63 (in flight during the first half)
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-                uint32_t v[32];
-                tmem_ld_32x32(treg + 128 + hh * 32, v);
-                tmem_ld_wait();
+                const uint32_t (&v)[32] = hh ? va : vb;
+                if (hh) tmem_ld_wait();
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const uint4 vv = vrow[hh * 4 + c];
@@ -304,9 +373,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
                     uint32_t o[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float a = fmaf(e256, bf_lo(w[j]), __uint_as_float(v[c * 8 + 2 * j])) * inv;
-                        const float b = fmaf(e256, bf_hi(w[j]), __uint_as_float(v[c * 8 + 2 * j + 1])) * inv;
-                        o[j] = pack2_bf16(a, b);
+                        float a, b, a2, b2;
+                        fmul2(a, b, bf_lo(w[j]), bf_hi(w[j]), ei, ei);
+                        ffma2(a2, b2, __uint_as_float(v[c * 8 + 2 * j]), __uint_as_float(v[c * 8 + 2 * j + 1]), inv, inv, a, b);
+                        o[j] = pack2_bf16(a2, b2);
                     }
                     reinterpret_cast<uint4*>(orow)[hh * 4 + c] = make_uint4(o[0], o[1], o[2], o[3]);
                 }

@@ -44,7 +44,21 @@ struct GemmCfg {
     static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU (torch.nn.GELU() default, bert.py:29,413) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, the
+// accuracy class of erff itself) on two MUFU ops (rcp, ex2) + 11 FMA-pipe ops instead of erff's ~30: the GELU epilogue of the
+// MLP up-projection is issue-bound, not MMA-bound, with erff.
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    float t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    float q = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+    q = fmaf(q, t, 0.5f * 1.421413741f);
+    q = fmaf(q, t, 0.5f * -0.284496736f);
+    q = fmaf(q, t, 0.5f * 0.254829592f);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((x * x) * -0.72134752044448170f));   // exp(-z^2)
+    const float h = (q * t) * e;                   // 0.5 * erfc(z) = 1 - Phi(|x|)
+    return fmaf(-fabsf(x), h, fmaxf(x, 0.f));      // x > 0: x - x h ; x < 0: x h
+}
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(384, 1)

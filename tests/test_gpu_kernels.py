@@ -88,7 +88,7 @@ def test_gemm_rejects_bad_shapes():
     assert rc == -1 and b"gemm shape" in _lib.lib().mb_last_error()
 
 
-@pytest.mark.parametrize("n_seq,S", [(1, 257), (3, 257), (2, 256), (2, 65), (1, 272)])
+@pytest.mark.parametrize("n_seq,S", [(1, 257), (3, 257), (40, 257), (2, 256), (2, 65), (1, 272)])
 def test_attention(n_seq, S):
     D, H = 1024, 16
     g = torch.Generator(device="cuda").manual_seed(S + n_seq)
@@ -99,9 +99,9 @@ def test_attention(n_seq, S):
     q, k, v = qkv.double().view(n_seq, S, 3, H, 64).permute(2, 0, 3, 1, 4)
     att = torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1)
     ref = (att @ v).permute(0, 2, 1, 3).reshape(n_seq * S, D)
-    err = (out.double() - ref).abs().max().item()
-    # P is rounded to bf16 before P.V (2^-9 relative), output rounded to bf16: 1.5e-2 abs on |v| ~ 1.5
-    assert err <= 1.5e-2, f"attention max err {err}"
+    err = (out.double() - ref).abs()
+    # output rounded to bf16 (2^-9 relative, |o| up to ~6) + P rounded to bf16 before P.V (2^-9 relative on |v| ~ 1.5)
+    assert (err <= ref.abs() * 2 ** -8 + 8e-3).all(), f"attention max err {err.max().item()}"
 
 
 @pytest.mark.parametrize("rows", [1, 7, 257, 1028])
