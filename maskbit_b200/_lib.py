@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmaskbit_b200.so")
+LIB_PATH = os.environ.get("MASKBIT_B200_LIB") or os.path.join(_HERE, "csrc", "libmaskbit_b200.so")   # env: A/B builds in tools/
 
 MB_GENERATOR, MB_TOKENIZER = 0, 1
 

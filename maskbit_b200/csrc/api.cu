@@ -544,6 +544,9 @@ static int ensure_ws(mb_handle* h, int n_seq) {
     return 0;
 }
 
+static long long* g_attn_trace = nullptr;   // ATC_TRACE builds: device buffer [8][8][12] set by mb_test_attention_trace
+extern "C" int mb_test_attention_trace(long long* device_buf) { g_attn_trace = device_buf; return 0; }
+
 // softmax(Q K^T / 8) V for every (sequence, head): the persistent tcgen05 kernel for the 257-token grid, the generic
 // mma.sync kernel for any other sequence length
 static int run_attention(mb_handle* h, const CUtensorMap& tm_big, const CUtensorMap& tm_row, const __nv_bfloat16* qkv,
@@ -552,7 +555,7 @@ static int run_attention(mb_handle* h, const CUtensorMap& tm_big, const CUtensor
     ProfScope prof(h, MB_PROF_ATTENTION, st);
     if (S == 257) {
         AttnTcParams p;
-        p.out = out; p.n_items = n_seq * H; p.H = H; p.D = D; p.sl2 = sl2;
+        p.out = out; p.n_items = n_seq * H; p.H = H; p.D = D; p.sl2 = sl2; p.trace = g_attn_trace;
         const int grid = p.n_items < num_sms ? p.n_items : num_sms;
         attention_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM_BYTES, st>>>(tm_big, tm_row, p);
     } else {

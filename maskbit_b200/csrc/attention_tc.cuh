@@ -2,25 +2,46 @@
 // (reference: nn.MultiheadAttention inside BertAttention, bert.py:84,137 -- softmax(Q K^T / 8) V per head, no mask, no cache)
 //
 // grid = #SMs, one CTA per SM looping over (sequence, head) work items; 12 warps:
-//   warp 0      TMA producer: Q / K / V of the item (3 x 256 rows x 64 dims, 128B swizzle) + the class-token rows
-//               (row 256 of Q, K, V) into a 2-stage shared-memory ring
-//   warp 1      MMA issuer (one thread): per 128-query tile t:  S_t = Q_t K^T  (tcgen05.mma M128 N256 K64, smem x smem)
-//                                                               O_t = P_t V    (A = P from TMEM, B = V MN-major from smem)
-//   warps 2,3   class-token query row (q = 256) on CUDA cores, alternating items: 257 dot products, softmax, 257-term
-//               weighted V sum; warp 3 also allocates TMEM (512 columns)
-//   warps 4-11  softmax: warpgroup t owns query tile t, thread = one query row.  Two passes over S_t in TMEM
-//               (max, then exp2 -> bf16 P written back over S), then (O_t + p256 v256) / l -> bf16 -> global.
-//               The class-token KEY (k = 256) is a rank-1 side path: its score column comes from a 16-wide MMA
-//               (Q_t x K[256..271]^T, column 0 used) issued with P V, its P*V is added in the epilogue.  Row sums l are
-//               also produced by the tensor core (P x ones) so that the exp loop is FFMA2 + MUFU + F2FP only.
-// TMEM per query tile (256 columns): [0,128) P as packed bf16x2 (aliases S columns already consumed), [128,192) O,
-//               [192,208) class-key scores, [208,224) row sums.
-// 257 = 2*128 + 1: tensor tiles cover the 256x256 block exactly; the odd row and column never touch a padded MMA tile.
+//   warp 0      TMA producer: Q / K / V of the item (3 x 256 rows x 64 dims, 128B swizzle) + 16-row boxes holding the
+//               class-token rows (row 256 of Q, K, V) into a 2-stage shared-memory ring
+//   warp 1      MMA issuer (one thread), data driven: per 128-query tile t
+//                   S_t = Q_t K^T            tcgen05.mma M128 N256 K16 x4, smem x smem
+//                   O_t = P_t V              A = P from TMEM, B = V MN-major from smem, 16 K-steps split over two
+//                                            accumulators (even / odd steps): dependent small MMAs are latency bound
+//   warps 2,3   the 257th row and column, alternating items, on warp-level mma.sync tiles:
+//                   s256[q] = Q[q] . K[256] for the 256 tile queries -> smem (the class-token KEY column)
+//                   the class-token QUERY row q = 256 against all 257 keys, softmax, P V -> global
+//               warp 3 also allocates TMEM (512 columns)
+//   warps 4-11  softmax: warpgroup t owns query tile t, thread = one query row.  Pass 1 row max over S_t in TMEM,
+//               pass 2 exp2 -> bf16 P written back over the S columns already consumed (FFMA2 + MUFU + F2FP + FADD2),
+//               epilogue (O_a + O_b + p256 V[256]) / l -> bf16 -> global.  The two warpgroups take turns in pass 2
+//               (named-barrier ping-pong) so each has the MUFU pipe to itself while the other waits on its MMAs.
+// TMEM per query tile (256 columns): S fp32 [0,256) -> P packed bf16x2 [0,128), O_a [128,192), O_b [192,256).
+// 257 = 2*128 + 1: tensor tiles cover the 256x256 block exactly; the odd row and column never touch a padded tcgen05 tile.
 //
 // Input  qkv  bf16 [rows, 3*D] through two TMA maps (box 64x256 and box 64x16); head h at columns h*64 of each third
 // Output out  bf16 [n_seq*257, D]
 #pragma once
+#include "attention.cuh"   // ldsm_x4, ldsm_x4_t, mma_bf16_16816
 #include "ptx.cuh"
+
+#ifndef ATC_TRACE
+#define ATC_TRACE 0            // 1: block 0 records (role, event, item, clock) tuples into AttnTcParams::trace
+#endif
+#if ATC_TRACE
+#define ATC_EV(role, ev, it)                                                                                       \
+    do {                                                                                                           \
+        if (blockIdx.x == 0 && p.trace && (it) < 12) {                                                             \
+            long long* _t = p.trace + (((role) * 8 + (ev)) * 12 + (it));                                           \
+            *_t = clock64();                                                                                       \
+        }                                                                                                          \
+    } while (0)
+#else
+#define ATC_EV(role, ev, it) do {} while (0)
+#endif
+#ifndef ATC_PINGPONG
+#define ATC_PINGPONG 0      // named-barrier turn-taking of the two softmax warpgroups in pass 2: measured slower (0.417 vs 0.365 ms)
+#endif
 
 namespace mb {
 
@@ -28,8 +49,8 @@ constexpr int ATC_THREADS = 384;
 constexpr int ATC_TILE_BYTES = 256 * 128;             // 256 rows x 64 bf16
 constexpr int ATC_ROW_BYTES = 16 * 128;               // 16-row box holding the class-token row in its first 128 B
 constexpr int ATC_STAGE_BYTES = 3 * ATC_TILE_BYTES + 3 * ATC_ROW_BYTES;
-constexpr int ATC_ONES_BYTES = 16 * 128;              // B operand of the row-sum MMA: 16 x 64 bf16 ones
-constexpr int ATC_SMEM_BYTES = 2 * ATC_STAGE_BYTES + ATC_ONES_BYTES + 1024 /*align*/ + 2304 /*p_cls*/ + 256 /*barriers*/;
+constexpr int ATC_S256_BYTES = 2 * 256 * 4;           // class-key scores of the 256 tile queries, per stage
+constexpr int ATC_SMEM_BYTES = 2 * ATC_STAGE_BYTES + ATC_S256_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 // D[tmem] (+)= A[tmem] * B[smem]
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -75,7 +96,7 @@ __device__ __forceinline__ float fast_exp2(float x) {   // MUFU.EX2; arguments h
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// packed fp32 pairs (FFMA2 / FMUL2 on sm_100): one issue slot for two lanes' worth of work
+// packed fp32 pairs (FFMA2 / FADD2 on sm_100): one issue slot for two elements
 __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
     asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
         "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
@@ -83,10 +104,10 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, 
         "mov.b64 {%0, %1}, rd;\n\t}"
         : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
 }
-__device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
     asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
         "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-        "mul.rn.f32x2 rd, ra, rb;\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\t"
         "mov.b64 {%0, %1}, rd;\n\t}"
         : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
@@ -98,20 +119,15 @@ __device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
 }
 // 16-byte chunk `ch` of row `r` inside a 128B-swizzled tile of 128-byte rows
 __device__ __forceinline__ uint32_t sw128(uint32_t tile, int r, int ch) { return tile + r * 128 + ((ch ^ (r & 7)) << 4); }
-
-__device__ __forceinline__ float dot8(uint4 a, uint4 b, float acc) {
-    acc = fmaf(bf_lo(a.x), bf_lo(b.x), acc); acc = fmaf(bf_hi(a.x), bf_hi(b.x), acc);
-    acc = fmaf(bf_lo(a.y), bf_lo(b.y), acc); acc = fmaf(bf_hi(a.y), bf_hi(b.y), acc);
-    acc = fmaf(bf_lo(a.z), bf_lo(b.z), acc); acc = fmaf(bf_hi(a.z), bf_hi(b.z), acc);
-    acc = fmaf(bf_lo(a.w), bf_lo(b.w), acc); acc = fmaf(bf_hi(a.w), bf_hi(b.w), acc);
-    return acc;
-}
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 struct AttnTcParams {
     __nv_bfloat16* out;   // [n_seq*257, D]
     int n_items;          // n_seq * H
     int H, D;
     float sl2;            // log2(e) / sqrt(64)
+    long long* trace;     // ATC_TRACE builds only: [roles 8][events 8][items 12] clock64 stamps of block 0
 };
 
 __global__ void __launch_bounds__(ATC_THREADS, 1)
@@ -120,16 +136,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
     extern __shared__ uint8_t atc_smem_raw[];
     const uint32_t raw = smem_u32(atc_smem_raw);
     uint8_t* base = atc_smem_raw + ((1024u - (raw & 1023u)) & 1023u);
-    uint32_t* ones = reinterpret_cast<uint32_t*>(base + 2 * ATC_STAGE_BYTES);        // 2 KB of bf16 1.0
-    float* p_cls = reinterpret_cast<float*>(base + 2 * ATC_STAGE_BYTES + ATC_ONES_BYTES);   // [2][288] class-row probabilities
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + 2 * ATC_STAGE_BYTES + ATC_ONES_BYTES + 2304);
-    uint64_t* full = bars;          // [2] TMA landed
-    uint64_t* empty = bars + 2;     // [2] stage consumed (MMA commit + 8 softmax warps + class warp)
-    uint64_t* s_full = bars + 4;    // [2] S_t complete in TMEM
-    uint64_t* p_full = bars + 6;    // [2] P_t written to TMEM (4 warps)
-    uint64_t* o_full = bars + 8;    // [2] O_t complete
-    uint64_t* t_free = bars + 10;   // [2] TMEM region t drained by the epilogue (4 warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    float* s256buf = reinterpret_cast<float*>(base + 2 * ATC_STAGE_BYTES);           // [2 stages][256 queries]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + 2 * ATC_STAGE_BYTES + ATC_S256_BYTES);
+    uint64_t* full = bars;           // [2] TMA landed
+    uint64_t* empty = bars + 2;      // [2] stage consumed (MMA commit + 8 softmax warps + class warp)
+    uint64_t* s_full = bars + 4;     // [2] S_t complete in TMEM
+    uint64_t* p_full = bars + 6;     // [2] P_t written to TMEM (4 warps)
+    uint64_t* o_full = bars + 8;     // [2] O_t complete
+    uint64_t* t_free = bars + 10;    // [2] TMEM region t drained by the epilogue (4 warps)
+    uint64_t* cls_ready = bars + 12; // [2] s256buf[stage] written by the class warp
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_big); tma_prefetch_desc(&tm_row); }
@@ -137,17 +153,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
         for (int s = 0; s < 2; ++s) {
             mbar_init(&full[s], 1); mbar_init(&empty[s], 10);
             mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 4); mbar_init(&o_full[s], 1); mbar_init(&t_free[s], 4);
+            mbar_init(&cls_ready[s], 1);
         }
         fence_mbar_init();
     }
     if (warp == 3) tmem_alloc<512>(tmem_slot);
-    for (int i = threadIdx.x; i < ATC_ONES_BYTES / 4; i += ATC_THREADS) ones[i] = 0x3f803f80u;
-    fence_async_proxy();                                    // generic-proxy smem writes -> visible to tcgen05.mma
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t smem0 = smem_u32(base);
+    const int n_local = p.n_items > (int)blockIdx.x ? (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     if (warp == 0) {
         if (lane == 0) {  // ---------------------------------------------------------------- TMA producer
@@ -158,59 +174,67 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
                 const int row0 = seq * S, col = head * 64;
                 uint8_t* sb = base + st * ATC_STAGE_BYTES;
                 mbar_wait(&empty[st], ph ^ 1);
+                ATC_EV(0, 0, it);
                 mbar_arrive_expect_tx(&full[st], ATC_STAGE_BYTES);
-                tma_load_2d(sb, &tm_big, &full[st], col, row0);                                          // Q rows 0..255
-                tma_load_2d(sb + ATC_TILE_BYTES, &tm_big, &full[st], p.D + col, row0);                   // K
+                tma_load_2d(sb + ATC_TILE_BYTES, &tm_big, &full[st], p.D + col, row0);                   // K rows 0..255
+                tma_load_2d(sb, &tm_big, &full[st], col, row0);                                          // Q
+                tma_load_2d(sb + 3 * ATC_TILE_BYTES, &tm_row, &full[st], col, row0 + 256);               // Q[256..]
+                tma_load_2d(sb + 3 * ATC_TILE_BYTES + ATC_ROW_BYTES, &tm_row, &full[st], p.D + col, row0 + 256);      // K[256..]
                 tma_load_2d(sb + 2 * ATC_TILE_BYTES, &tm_big, &full[st], 2 * p.D + col, row0);           // V
-                tma_load_2d(sb + 3 * ATC_TILE_BYTES, &tm_row, &full[st], col, row0 + 256);               // Q[256]
-                tma_load_2d(sb + 3 * ATC_TILE_BYTES + ATC_ROW_BYTES, &tm_row, &full[st], p.D + col, row0 + 256);      // K[256]
-                tma_load_2d(sb + 3 * ATC_TILE_BYTES + 2 * ATC_ROW_BYTES, &tm_row, &full[st], 2 * p.D + col, row0 + 256);  // V[256]
+                tma_load_2d(sb + 3 * ATC_TILE_BYTES + 2 * ATC_ROW_BYTES, &tm_row, &full[st], 2 * p.D + col, row0 + 256);  // V[256..]
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {  // ---------------------------------------------------------------- MMA issuer
             constexpr uint32_t idesc_s = make_idesc(1, 128, 256);
             constexpr uint32_t idesc_o = make_idesc(1, 128, 64) | (1u << 16);   // B (= V) is MN-major
-            constexpr uint32_t idesc_16 = make_idesc(1, 128, 16);
-            const uint64_t ones_desc = make_sdesc_k128(smem0 + 2 * ATC_STAGE_BYTES);
-            uint32_t it = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-                const int st = it & 1; const uint32_t ph = (it >> 1) & 1, ip = it & 1;
-                const uint32_t sq = smem0 + st * ATC_STAGE_BYTES, sk = sq + ATC_TILE_BYTES, sv = sk + ATC_TILE_BYTES;
-                mbar_wait(&full[st], ph);
-                tc_fence_after();
+            // Data-driven issue order: the two query tiles are independent pipelines (S_t -> softmax -> P_t V -> epilogue);
+            // whichever MMA group has its inputs ready is issued next (non-blocking barrier probes).
+            int it_s[2] = {0, 0}, it_p[2] = {0, 0};
+            long long t_poll = clock64();
+            while (it_p[0] < n_local || it_p[1] < n_local) {
+                bool progressed = false;
 #pragma unroll
-                for (int t = 0; t < 2; ++t) {                       // S_t = Q_t K^T
-                    mbar_wait(&t_free[t], ip ^ 1);
-                    tc_fence_after();
-                    const uint64_t a = make_sdesc_k128(sq + t * 128 * 128), b = make_sdesc_k128(sk);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16(tmem_base + t * 256, a + 2 * k, b + 2 * k, idesc_s, k != 0);
-                    umma_commit(&s_full[t]);
-                }
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {                       // O_t = P_t V
-                    mbar_wait(&p_full[t], ip);
-                    tc_fence_after();
-                    const uint64_t b = make_sdesc_mn128(sv);
+                for (int t = 0; t < 2; ++t) {
                     const uint32_t tr = tmem_base + t * 256;
+                    if (it_s[t] < n_local && it_s[t] == it_p[t]) {                 // S_t = Q_t K^T of item it_s[t]
+                        const int it = it_s[t], st = it & 1;
+                        if (mbar_test_wait(&full[st], (it >> 1) & 1) && mbar_test_wait(&t_free[t], (it & 1) ^ 1)) {
+                            tc_fence_after();
+                            const uint32_t sq = smem0 + st * ATC_STAGE_BYTES, sk = sq + ATC_TILE_BYTES;
+                            const uint64_t a = make_sdesc_k128(sq + t * 128 * 128), b = make_sdesc_k128(sk);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        umma_f16_ts(tr + 128, tr + 8 * j, b + (uint64_t)(j * 128), idesc_o, j != 0);      // O += P_j V_j
-                        umma_f16_ts(tr + 208, tr + 8 * j, ones_desc, idesc_16, j != 0);                   // l += P_j 1
+                            for (int k = 0; k < 4; ++k) umma_f16(tr, a + 2 * k, b + 2 * k, idesc_s, k != 0);
+                            umma_commit(&s_full[t]);
+                            ATC_EV(1, t, it);
+                            it_s[t]++; progressed = true;
+                        }
                     }
-                    const uint64_t a = make_sdesc_k128(sq + t * 128 * 128), kc16 = make_sdesc_k128(sq + 3 * ATC_TILE_BYTES + ATC_ROW_BYTES);
+                    if (it_p[t] < it_s[t]) {                                       // O_t = P_t V
+                        const int it = it_p[t], st = it & 1;
+                        if (mbar_test_wait(&p_full[t], it & 1)) {
+                            tc_fence_after();
+                            const uint64_t b = make_sdesc_mn128(smem0 + st * ATC_STAGE_BYTES + 2 * ATC_TILE_BYTES);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16(tr + 192, a + 2 * k, kc16 + 2 * k, idesc_16, k != 0);  // Q_t K[256..]^T
-                    umma_commit(&o_full[t]);
+                            for (int j = 0; j < 16; ++j)       // even key blocks -> O_a, odd -> O_b: two independent chains
+                                umma_f16_ts(tr + 128 + 64 * (j & 1), tr + 8 * j, b + (uint64_t)(j * 128), idesc_o, j >= 2);
+                            umma_commit(&o_full[t]);
+                            ATC_EV(1, 2 + t, it);
+                            it_p[t]++; progressed = true;
+                            if (it_p[t ^ 1] > it) umma_commit(&empty[st]);         // both tiles of the item have read the stage
+                        }
+                    }
                 }
-                umma_commit(&empty[st]);
+                if (progressed) t_poll = clock64();
+                else if (clock64() - t_poll > MB_WAIT_TIMEOUT_CYCLES) { printf("attention MMA issuer timeout: block %d\n", (int)blockIdx.x); __trap(); }
             }
         }
-    } else if (warp == 2 || warp == 3) {  // -------------------------------------------- class-token query row
-        // warps 2 and 3 alternate work items (each item's class row costs ~2.5k instructions of one warp)
-        float* pc = p_cls + (warp - 2) * 288;
+    } else if (warp == 2 || warp == 3) {  // -------------------------------------------- the 257th row and column
+        // One query row / one key column is too small for a tcgen05 tile and too slow as scalar FMAs, so both run on the
+        // warp-level tensor path: mma.sync m16n8k16 with a single live row (or column) in one operand, the other operand
+        // via ldmatrix from the swizzled TMA tiles.  Warps 2 and 3 alternate work items.
         uint32_t it = 0;
+        const int g = lane >> 2, t4 = lane & 3;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
             if ((it & 1) != (uint32_t)(warp - 2)) continue;
             const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
@@ -218,86 +242,106 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
             const uint32_t sq = smem0 + st * ATC_STAGE_BYTES, sk = sq + ATC_TILE_BYTES, sv = sk + ATC_TILE_BYTES;
             const uint32_t qc = sq + 3 * ATC_TILE_BYTES, kc = qc + ATC_ROW_BYTES, vc = kc + ATC_ROW_BYTES;
             mbar_wait(&full[st], ph);
-            float q[64];
+            if (lane == 0) ATC_EV(2, 0, it);
+            // ---- class-key column: s256[q] = Q[q] . K[256], q = 0..255.  A = 16 query rows, B = K[256] in column n = 0.
+            {
+                uint32_t kb[4][2];                      // B fragments: b0 = dims 16kk+2t,+1 ; b1 = dims 16kk+8+2t,+1 (n = g = 0 only)
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const uint4 w = lds128(qc + c * 16);
-                q[8 * c + 0] = bf_lo(w.x); q[8 * c + 1] = bf_hi(w.x); q[8 * c + 2] = bf_lo(w.y); q[8 * c + 3] = bf_hi(w.y);
-                q[8 * c + 4] = bf_lo(w.z); q[8 * c + 5] = bf_hi(w.z); q[8 * c + 6] = bf_lo(w.w); q[8 * c + 7] = bf_hi(w.w);
-            }
-            auto qdot = [&](uint32_t row_addr, int rsw) {
-                float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint4 w = lds128(row_addr + ((c ^ rsw) << 4));
-                    a0 = fmaf(q[8 * c + 0], bf_lo(w.x), a0); a1 = fmaf(q[8 * c + 1], bf_hi(w.x), a1);
-                    a0 = fmaf(q[8 * c + 2], bf_lo(w.y), a0); a1 = fmaf(q[8 * c + 3], bf_hi(w.y), a1);
-                    a0 = fmaf(q[8 * c + 4], bf_lo(w.z), a0); a1 = fmaf(q[8 * c + 5], bf_hi(w.z), a1);
-                    a0 = fmaf(q[8 * c + 6], bf_lo(w.w), a0); a1 = fmaf(q[8 * c + 7], bf_hi(w.w), a1);
+                for (int kk = 0; kk < 4; ++kk) {
+                    kb[kk][0] = g == 0 ? lds32(kc + (kk * 8 + t4) * 4) : 0u;
+                    kb[kk][1] = g == 0 ? lds32(kc + (kk * 8 + 4 + t4) * 4) : 0u;
                 }
-                return a0 + a1;
-            };
-            float sc[9];
-#pragma unroll
-            for (int r = 0; r < 8; ++r) sc[r] = qdot(sk + (lane + 32 * r) * 128, lane & 7);
-            sc[8] = qdot(kc, 0);                            // key 256 (same value in every lane)
-            float mx = sc[8];
-#pragma unroll
-            for (int r = 0; r < 8; ++r) mx = fmaxf(mx, sc[r]);
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            const float ms = mx * p.sl2;
-            float sum = 0.f;
-            __syncwarp();                                   // previous readers of pc are done
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const float e = fast_exp2(fmaf(sc[r], p.sl2, -ms));
-                sum += e;
-                pc[lane + 32 * r] = e;
-            }
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            const float e256 = fast_exp2(fmaf(sc[8], p.sl2, -ms));
-            sum += e256;
-            __syncwarp();
-            // P V: lane = (key group kg = lane >> 3: keys kg, kg+4, ...; dim chunk dc = lane & 7: dims 8dc..8dc+7)
-            const int kg = lane >> 3, dc = lane & 7;
-            float o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = 0.f;
+                float* dst = s256buf + st * 256;
 #pragma unroll 4
-            for (int i = 0; i < 64; ++i) {
-                const int key = kg + 4 * i;
-                const float pk = pc[key];
-                const uint4 w = lds128(sw128(sv, key, dc));
-                o[0] = fmaf(pk, bf_lo(w.x), o[0]); o[1] = fmaf(pk, bf_hi(w.x), o[1]);
-                o[2] = fmaf(pk, bf_lo(w.y), o[2]); o[3] = fmaf(pk, bf_hi(w.y), o[3]);
-                o[4] = fmaf(pk, bf_lo(w.z), o[4]); o[5] = fmaf(pk, bf_hi(w.z), o[5]);
-                o[6] = fmaf(pk, bf_lo(w.w), o[6]); o[7] = fmaf(pk, bf_hi(w.w), o[7]);
-            }
+                for (int mt = 0; mt < 16; ++mt) {
+                    float c[4] = {0.f, 0.f, 0.f, 0.f};
+                    const int r = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                o[j] += __shfl_xor_sync(0xffffffffu, o[j], 8);
-                o[j] += __shfl_xor_sync(0xffffffffu, o[j], 16);
+                    for (int kk = 0; kk < 4; ++kk) {
+                        uint32_t a[4];
+                        ldsm_x4(a, sw128(sq, r, kk * 2 + (lane >> 4)));
+                        mma_bf16_16816(c, a, kb[kk][0], kb[kk][1]);
+                    }
+                    if (t4 == 0) { dst[mt * 16 + g] = c[0]; dst[mt * 16 + g + 8] = c[2]; }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&cls_ready[st]);
             }
-            if (kg == 0) {
-                const uint4 w = lds128(vc + dc * 16);
+            // ---- class-query row.  A fragments of q_cls for the 4 k-steps: a0 = dims 16kk+2t,+1 ; a2 = dims 16kk+8+2t,+1 (row 0)
+            uint32_t qa[4][4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                qa[kk][0] = g == 0 ? lds32(qc + (kk * 8 + t4) * 4) : 0u;
+                qa[kk][2] = g == 0 ? lds32(qc + (kk * 8 + 4 + t4) * 4) : 0u;
+                qa[kk][1] = 0u; qa[kk][3] = 0u;
+            }
+            // scores: 33 n-tiles of 8 keys (tile 32 = keys 256..263 from the class-row box; only key 256 is real)
+            float sc[33][2];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < 33; ++nt) {
+                float c[4] = {0.f, 0.f, 0.f, 0.f};
+                const uint32_t tile = nt < 32 ? sk : kc;
+                const int r = (nt < 32 ? nt * 8 : 0) + (lane & 7);
+#pragma unroll
+                for (int kp = 0; kp < 2; ++kp) {
+                    uint32_t b[4];
+                    ldsm_x4(b, sw128(tile, r, kp * 4 + (lane >> 3)));
+                    mma_bf16_16816(c, qa[2 * kp], b[0], b[1]);
+                    mma_bf16_16816(c, qa[2 * kp + 1], b[2], b[3]);
+                }
+                if (nt == 32) { if (t4 != 0) c[0] = -INFINITY; c[1] = -INFINITY; }      // keys 257.. do not exist
+                sc[nt][0] = c[0]; sc[nt][1] = c[1];
+                mx = fmaxf(mx, fmaxf(c[0], c[1]));
+            }
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            const float nms = -mx * p.sl2;
+            float sum = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 33; ++nt) {
+                sc[nt][0] = fast_exp2(fmaf(sc[nt][0], p.sl2, nms));
+                sc[nt][1] = fast_exp2(fmaf(sc[nt][1], p.sl2, nms));
+                sum += sc[nt][0] + sc[nt][1];
+            }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            // O = P V: 17 k-tiles of 16 keys (tile 16 = keys 256..271 from the class-row box, P = 0 beyond key 256)
+            float o[8][4];
+#pragma unroll
+            for (int dt = 0; dt < 8; ++dt) { o[dt][0] = 0.f; o[dt][1] = 0.f; o[dt][2] = 0.f; o[dt][3] = 0.f; }
+#pragma unroll
+            for (int kt = 0; kt < 17; ++kt) {
+                uint32_t pa[4];
+                pa[0] = pack2_bf16(sc[2 * kt][0], sc[2 * kt][1]);
+                pa[2] = kt < 16 ? pack2_bf16(sc[2 * kt + 1][0], sc[2 * kt + 1][1]) : 0u;
+                pa[1] = 0u; pa[3] = 0u;
+                const uint32_t tile = kt < 16 ? sv : vc;
+                const int r = (kt < 16 ? kt * 16 : 0) + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+                for (int dp = 0; dp < 4; ++dp) {
+                    uint32_t b[4];
+                    ldsm_x4_t(b, sw128(tile, r, dp * 2 + (lane >> 4)));
+                    mma_bf16_16816(o[2 * dp], pa, b[0], b[1]);
+                    mma_bf16_16816(o[2 * dp + 1], pa, b[2], b[3]);
+                }
+            }
+            if (g == 0) {
                 const float inv = 1.0f / sum;
-                uint4 r;
-                r.x = pack2_bf16(fmaf(e256, bf_lo(w.x), o[0]) * inv, fmaf(e256, bf_hi(w.x), o[1]) * inv);
-                r.y = pack2_bf16(fmaf(e256, bf_lo(w.y), o[2]) * inv, fmaf(e256, bf_hi(w.y), o[3]) * inv);
-                r.z = pack2_bf16(fmaf(e256, bf_lo(w.z), o[4]) * inv, fmaf(e256, bf_hi(w.z), o[5]) * inv);
-                r.w = pack2_bf16(fmaf(e256, bf_lo(w.w), o[6]) * inv, fmaf(e256, bf_hi(w.w), o[7]) * inv);
-                __nv_bfloat16* orow = p.out + ((size_t)seq * S + 256) * p.D + head * 64;
-                reinterpret_cast<uint4*>(orow)[dc] = r;
+                __nv_bfloat16* orow = p.out + ((size_t)seq * S + 256) * p.D + head * 64 + 2 * t4;
+#pragma unroll
+                for (int dt = 0; dt < 8; ++dt) *reinterpret_cast<uint32_t*>(orow + dt * 8) = pack2_bf16(o[dt][0] * inv, o[dt][1] * inv);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[st]);
+            if (lane == 0) { mbar_arrive(&empty[st]); ATC_EV(2, 1, it); }
         }
     } else if (warp >= 4) {  // ------------------------------------------------------------ softmax + epilogue
         const int t = (warp - 4) >> 2, quarter = warp & 3;
         const int row = t * 128 + quarter * 32 + lane;                 // query row inside the sequence (0..255)
         const uint32_t treg = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * 256;
+#if ATC_PINGPONG
+        if (t == 1) named_bar_arrive(1, 256);                          // warpgroup 0 takes the first turn in pass 2
+#endif
         uint32_t it = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
             const int st = it & 1; const uint32_t ph = (it >> 1) & 1, ip = it & 1;
@@ -305,7 +349,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
             const uint32_t vc = smem0 + st * ATC_STAGE_BYTES + 3 * ATC_TILE_BYTES + 2 * ATC_ROW_BYTES;
             mbar_wait(&s_full[t], ip);
             tc_fence_after();
-            float mx = -INFINITY;
+            if (quarter == 0 && lane == 0) ATC_EV(3 + t, 0, it);
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             uint32_t va[32], vb[32];
             // pass 1: row max over keys 0..255.  The load of chunk c+1 is in flight while chunk c is reduced.
             tmem_ld_32x32(treg, va);
@@ -314,22 +359,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
             for (int c = 0; c < 8; c += 2) {
                 tmem_ld_32x32(treg + (c + 1) * 32, vb);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(va[j]));
+                for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(va[j]));
                 tmem_ld_wait();
                 tmem_ld_32x32(treg + ((c + 2) & 7) * 32, va);      // wraps to chunk 0: first chunk of pass 2
 #pragma unroll
-                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(vb[j]));
+                for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(vb[j]));
                 tmem_ld_wait();
             }
-            const float nms = -mx * p.sl2;
+            mbar_wait(&cls_ready[st], ph);
+            const float s256 = s256buf[st * 256 + row];                // score against the class-token key
+            const float nms = -fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])), s256) * p.sl2;
+            if (quarter == 0 && lane == 0) ATC_EV(3 + t, 1, it);
+#if ATC_PINGPONG
+            named_bar_sync(1 + t, 256);                                // my turn on the MUFU pipe
+#endif
             // pass 2: p = exp2(s * sl2 - max * sl2) -> bf16 pairs written over S columns already consumed
+            float sum0 = 0.f, sum1 = 0.f;
             auto exp_store = [&](const uint32_t (&v)[32], int c) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     float x0, x1;
                     ffma2(x0, x1, __uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), p.sl2, p.sl2, nms, nms);
-                    pk[j] = pack2_bf16(fast_exp2(x0), fast_exp2(x1));
+                    x0 = fast_exp2(x0); x1 = fast_exp2(x1);
+                    fadd2(sum0, sum1, sum0, sum1, x0, x1);
+                    pk[j] = pack2_bf16(x0, x1);
                 }
                 tmem_st_32x32_x16(treg + c * 16, pk);
             };
@@ -342,41 +396,41 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
                 exp_store(vb, c + 1);
                 if (c + 2 < 8) tmem_ld_wait();
             }
+#if ATC_PINGPONG
+            named_bar_arrive(1 + (t ^ 1), 256);                        // hand the MUFU pipe to the other warpgroup
+#endif
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[t]);
-            // epilogue: (O_t + p256 * V[256]) / (l + p256) -> bf16 row
+            if (quarter == 0 && lane == 0) ATC_EV(3 + t, 2, it);
+            // epilogue: (O_a + O_b + p256 * V[256]) / (l + p256) -> bf16 row
+            const float e256 = fast_exp2(fmaf(s256, p.sl2, nms));
+            const float inv = 1.0f / (sum0 + sum1 + e256);
+            const float ei = e256 * inv;
             mbar_wait(&full[st], ph);                                  // (long complete) makes the TMA-written V[256] row visible
-            uint4 vrow[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) vrow[c] = lds128(vc + c * 16);
+            __nv_bfloat16* orow = p.out + ((size_t)seq * S + row) * p.D + head * 64;
             mbar_wait(&o_full[t], ip);
             tc_fence_after();
-            tmem_ld_32x32(treg + 192, va);                             // [0] class-key score, [16] row sum
-            tmem_ld_32x32(treg + 128, vb);                             // O columns 0..31
-            tmem_ld_wait();
-            // exponent clamped: if the class key dominates by more than 2^100 the result is V[256] to fp32 precision anyway
-            const float e256 = fast_exp2(fminf(fmaf(__uint_as_float(va[0]), p.sl2, nms), 100.0f));
-            const float inv = 1.0f / (__uint_as_float(va[16]) + e256);
-            const float ei = e256 * inv;
-            __nv_bfloat16* orow = p.out + ((size_t)seq * S + row) * p.D + head * 64;
-            tmem_ld_32x32(treg + 160, va);                             // O columns 32..63 (in flight during the first half)
+            if (quarter == 0 && lane == 0) ATC_EV(3 + t, 3, it);
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-                const uint32_t (&v)[32] = hh ? va : vb;
-                if (hh) tmem_ld_wait();
+                tmem_ld_32x32(treg + 128 + hh * 32, va);               // O_a columns 32hh..32hh+31
+                tmem_ld_32x32(treg + 192 + hh * 32, vb);               // O_b
+                tmem_ld_wait();
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const uint4 vv = vrow[hh * 4 + c];
+                    const uint4 vv = lds128(vc + (hh * 4 + c) * 16);
                     const uint32_t w[4] = {vv.x, vv.y, vv.z, vv.w};
                     uint32_t o[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        float a, b, a2, b2;
-                        fmul2(a, b, bf_lo(w[j]), bf_hi(w[j]), ei, ei);
-                        ffma2(a2, b2, __uint_as_float(v[c * 8 + 2 * j]), __uint_as_float(v[c * 8 + 2 * j + 1]), inv, inv, a, b);
-                        o[j] = pack2_bf16(a2, b2);
+                        float a, b;
+                        fadd2(a, b, __uint_as_float(va[c * 8 + 2 * j]), __uint_as_float(va[c * 8 + 2 * j + 1]),
+                              __uint_as_float(vb[c * 8 + 2 * j]), __uint_as_float(vb[c * 8 + 2 * j + 1]));
+                        a = fmaf(a, inv, bf_lo(w[j]) * ei);
+                        b = fmaf(b, inv, bf_hi(w[j]) * ei);
+                        o[j] = pack2_bf16(a, b);
                     }
                     reinterpret_cast<uint4*>(orow)[hh * 4 + c] = make_uint4(o[0], o[1], o[2], o[3]);
                 }
@@ -384,6 +438,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive(&t_free[t]); mbar_arrive(&empty[st]); }
+            if (quarter == 0 && lane == 0) ATC_EV(3 + t, 4, it);
         }
     }
     __syncwarp();
