@@ -60,7 +60,8 @@ SYMBOLS = {
     "mb_profile_read": (_I, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64), _I]),
     "mb_test_gemm": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "mb_test_attention": (_I, [_P, _P, _I, _I, _I, _I, _P]),
-    "mb_test_layernorm": (_I, [_P, _P, _P, _F, _P, _I, _I, _P]),
+    "mb_test_attention_trace": (_I, [_P]),
+    "mb_test_gemm_ex": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
 }
 
 PROF_KINDS = ["embed_ln", "gemm_qkv", "attention", "gemm_out", "layernorm", "gemm_up", "gemm_down", "gemm_head", "select",

@@ -87,6 +87,34 @@ __global__ void transpose_f32_kernel(const float* __restrict__ in, float* __rest
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // in [rows, cols] -> out [cols, rows]
     if (i < (size_t)rows * cols) { int r = (int)(i / cols), c = (int)(i % cols); out[(size_t)c * rows + r] = in[i]; }
 }
+// LayerNorm folded into the Linear that consumes it (gemm_tcgen05.cuh): one block per output feature n
+//   wout[n,k] = bf16(w[n,k] * gamma[k]);  u[n] = sum_k float(wout[n,k]);  c[n] = sum_k w[n,k] * beta[k] + bias[n]
+__global__ void __launch_bounds__(256)
+fold_ln_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
+               const float* __restrict__ bias, __nv_bfloat16* __restrict__ wout, float* __restrict__ u, float* __restrict__ c, int K) {
+    const int n = blockIdx.x;
+    float su = 0.f, sc = 0.f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const float wv = w[(size_t)n * K + k];
+        const __nv_bfloat16 wg = __float2bfloat16_rn(wv * gamma[k]);
+        wout[(size_t)n * K + k] = wg;
+        su += __bfloat162float(wg);
+        sc = fmaf(wv, beta[k], sc);
+    }
+    __shared__ float r0[8], r1[8];
+    su = warp_sum(su); sc = warp_sum(sc);
+    if ((threadIdx.x & 31) == 0) { r0[threadIdx.x >> 5] = su; r1[threadIdx.x >> 5] = sc; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int i = 0; i < 8; ++i) { a += r0[i]; b += r1[i]; }
+        u[n] = a; c[n] = b + bias[n];
+    }
+}
+__global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + b[i];
+}
 // conv weight fp32 [Cout][Cin][kh][kw] -> split bf16 hi/lo [Cout][tap*Cin + c]
 __global__ void pack_conv_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                  int cout, int cin, int taps) {
@@ -131,8 +159,9 @@ __global__ void fill_i64_kernel(int64_t* p, size_t n, int64_t v) {
 // ------------------------------------------------------------------------------------------------ handle
 struct DevTensor { float* ptr = nullptr; std::vector<int64_t> shape; size_t numel = 0; };
 
+// b / v2 follow GemmParams::bias / vec2: plain (bias, -), LN-in (c, u), residual (bias + beta_res, gamma_res)
 struct Linear {
-    __nv_bfloat16* w = nullptr; float* b = nullptr; int N = 0, K = 0, BN = 0; CUtensorMap tm;
+    __nv_bfloat16* w = nullptr; float* b = nullptr; float* v2 = nullptr; int N = 0, K = 0, BN = 0; CUtensorMap tm;
 };
 struct LNW { float* g = nullptr; float* b = nullptr; };
 struct Layer { Linear qkv, out, up, down; LNW ln1, ln2; };
@@ -156,9 +185,10 @@ struct mb_handle {
     Linear head, pred;
     // generator workspace
     int cap_seqs = 0; size_t cap_rows = 0;
-    __nv_bfloat16 *x = nullptr, *qkv = nullptr, *att = nullptr, *hmid = nullptr;
-    float* pre = nullptr;
-    CUtensorMap tm_x, tm_att, tm_hmid, tm_qkv_big, tm_qkv_row;
+    // yA / yB: the residual stream as pre-LayerNorm sums (bf16) with per-row partial statistics stA / stB
+    __nv_bfloat16 *yA = nullptr, *yB = nullptr, *qkv = nullptr, *att = nullptr, *hmid = nullptr;
+    float2 *stA = nullptr, *stB = nullptr;
+    CUtensorMap tm_yA, tm_yB, tm_att, tm_hmid, tm_qkv_big, tm_qkv_row;
     // sampler workspace
     int cap_sample_B = 0;
     int64_t *tok_a = nullptr, *tok_b = nullptr, *pred_buf = nullptr, *combined = nullptr;
@@ -234,9 +264,9 @@ extern "C" int mb_create(const mb_config* cfg, mb_handle** out) {
 }
 
 static void free_ws(mb_handle* h) {
-    void* ps[] = {h->x, h->qkv, h->att, h->hmid, h->pre};
+    void* ps[] = {h->yA, h->yB, h->qkv, h->att, h->hmid, h->stA, h->stB};
     for (void* p : ps) if (p) cudaFree(p);
-    h->x = h->qkv = h->att = h->hmid = nullptr; h->pre = nullptr; h->cap_seqs = 0;
+    h->yA = h->yB = h->qkv = h->att = h->hmid = nullptr; h->stA = h->stB = nullptr; h->cap_seqs = 0;
 }
 static void free_sample_ws(mb_handle* h) {
     void* ps[] = {h->tok_a, h->tok_b, h->pred_buf, h->combined, h->logits_ws, h->drop_ws};
@@ -319,19 +349,46 @@ static int keep_f32(mb_handle* h, int model, const std::string& name, std::vecto
 }
 static int pick_bn(int N) { return N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 0)); }
 
-static int make_linear(mb_handle* h, const std::string& wname, const std::string& bname, int N, int K, Linear* L) {
-    DevTensor w;
+// Linear whose input is LayerNorm(y): fold gamma / beta of `ln` into the weights (see gemm_tcgen05.cuh)
+static int make_linear_lnin(mb_handle* h, const std::string& wname, const std::string& bname, int N, int K, const LNW& ln, Linear* L) {
+    DevTensor w, b;
     MB_TRY(take(h, MB_GENERATOR, wname, {N, K}, &w));
+    MB_TRY(take(h, MB_GENERATOR, bname, {N}, &b));
     L->N = N; L->K = K; L->BN = pick_bn(N);
     if (!L->BN || K % 64) return fail(MB_ERR_INVALID, "linear %s: N=%d K=%d not tileable", wname.c_str(), N, K);
     MB_TRY(dev_alloc(h, &L->w, (size_t)N * K));
-    f32_to_bf16_kernel<<<(unsigned)(((size_t)N * K + 255) / 256), 256>>>(w.ptr, L->w, (size_t)N * K);
+    MB_TRY(dev_alloc(h, &L->b, (size_t)N));
+    MB_TRY(dev_alloc(h, &L->v2, (size_t)N));
+    fold_ln_kernel<<<N, 256>>>(w.ptr, ln.g, ln.b, b.ptr, L->w, L->v2, L->b, K);
     CU_TRY(cudaGetLastError());
-    MB_TRY(keep_f32(h, MB_GENERATOR, bname, {N}, &L->b));
     MB_TRY(make_tmap_bf16(&L->tm, L->w, N, K, L->BN));
     CU_TRY(cudaDeviceSynchronize());
-    cudaFree(w.ptr);
-    h->staged[MB_GENERATOR].erase(wname);
+    cudaFree(w.ptr); cudaFree(b.ptr);
+    h->staged[MB_GENERATOR].erase(wname); h->staged[MB_GENERATOR].erase(bname);
+    return 0;
+}
+// Linear whose epilogue adds the residual LayerNorm_res(y_res): bias' = bias + beta_res, vec2 = gamma_res
+static int make_linear_res(mb_handle* h, const std::string& wname, const std::string& bname, int N, int K, const LNW& ln_res, Linear* L) {
+    DevTensor w, b;
+    MB_TRY(take(h, MB_GENERATOR, wname, {N, K}, &w));
+    MB_TRY(take(h, MB_GENERATOR, bname, {N}, &b));
+    L->N = N; L->K = K; L->BN = pick_bn(N);
+    if (L->BN != 256 || N != 1024 || K % 64) return fail(MB_ERR_INVALID, "linear %s: N=%d K=%d unsupported for the residual epilogue", wname.c_str(), N, K);
+    MB_TRY(dev_alloc(h, &L->w, (size_t)N * K));
+    MB_TRY(dev_alloc(h, &L->b, (size_t)N));
+    L->v2 = ln_res.g;
+    f32_to_bf16_kernel<<<(unsigned)(((size_t)N * K + 255) / 256), 256>>>(w.ptr, L->w, (size_t)N * K);
+    add_vec_kernel<<<(N + 255) / 256, 256>>>(b.ptr, ln_res.b, L->b, N);
+    CU_TRY(cudaGetLastError());
+    MB_TRY(make_tmap_bf16(&L->tm, L->w, N, K, L->BN));
+    CU_TRY(cudaDeviceSynchronize());
+    cudaFree(w.ptr); cudaFree(b.ptr);
+    h->staged[MB_GENERATOR].erase(wname); h->staged[MB_GENERATOR].erase(bname);
+    return 0;
+}
+static int keep_ln(mb_handle* h, const std::string& prefix, int D, LNW* ln) {
+    MB_TRY(keep_f32(h, MB_GENERATOR, prefix + ".weight", {D}, &ln->g));
+    MB_TRY(keep_f32(h, MB_GENERATOR, prefix + ".bias", {D}, &ln->b));
     return 0;
 }
 
@@ -347,25 +404,27 @@ static int finalize_generator(mb_handle* h) {
     MB_TRY(keep_f32(h, MB_GENERATOR, "input_proj.bias", {D}, &h->b_in));
     MB_TRY(keep_f32(h, MB_GENERATOR, "class_emb.weight", {c.nclass + 1, D}, &h->class_emb));
     MB_TRY(keep_f32(h, MB_GENERATOR, "pos_emb", {1, h->S, D}, &h->pos));
-    MB_TRY(keep_f32(h, MB_GENERATOR, "first_layer.0.weight", {D}, &h->ln_first.g));
-    MB_TRY(keep_f32(h, MB_GENERATOR, "first_layer.0.bias", {D}, &h->ln_first.b));
+    // every LayerNorm first: each one is folded into the Linears that consume its output
+    MB_TRY(keep_ln(h, "first_layer.0", D, &h->ln_first));
     h->layers.resize(c.depth);
     for (int l = 0; l < c.depth; ++l) {
         const std::string p = "transformer.layers." + std::to_string(l) + ".";
-        Layer& L = h->layers[l];
-        MB_TRY(make_linear(h, p + "0.mha.in_proj_weight", p + "0.mha.in_proj_bias", 3 * D, D, &L.qkv));
-        MB_TRY(make_linear(h, p + "0.mha.out_proj.weight", p + "0.mha.out_proj.bias", D, D, &L.out));
-        MB_TRY(keep_f32(h, MB_GENERATOR, p + "0.norm.weight", {D}, &L.ln1.g));
-        MB_TRY(keep_f32(h, MB_GENERATOR, p + "0.norm.bias", {D}, &L.ln1.b));
-        MB_TRY(make_linear(h, p + "1.net.0.weight", p + "1.net.0.bias", c.mlp_dim, D, &L.up));
-        MB_TRY(make_linear(h, p + "1.net.2.weight", p + "1.net.2.bias", D, c.mlp_dim, &L.down));
-        MB_TRY(keep_f32(h, MB_GENERATOR, p + "1.norm.weight", {D}, &L.ln2.g));
-        MB_TRY(keep_f32(h, MB_GENERATOR, p + "1.norm.bias", {D}, &L.ln2.b));
+        MB_TRY(keep_ln(h, p + "0.norm", D, &h->layers[l].ln1));
+        MB_TRY(keep_ln(h, p + "1.norm", D, &h->layers[l].ln2));
     }
-    MB_TRY(make_linear(h, "last_layer.0.weight", "last_layer.0.bias", D, D, &h->head));
-    MB_TRY(keep_f32(h, MB_GENERATOR, "last_layer.2.weight", {D}, &h->ln_head.g));
-    MB_TRY(keep_f32(h, MB_GENERATOR, "last_layer.2.bias", {D}, &h->ln_head.b));
-    MB_TRY(make_linear(h, "prediction_layer.weight", "prediction_layer.bias", c.codebook_splits * h->V, D, &h->pred));
+    MB_TRY(keep_ln(h, "last_layer.2", D, &h->ln_head));
+    for (int l = 0; l < c.depth; ++l) {
+        const std::string p = "transformer.layers." + std::to_string(l) + ".";
+        Layer& L = h->layers[l];
+        const LNW& ln_in = l == 0 ? h->ln_first : h->layers[l - 1].ln2;     // x_l = LN_in(y): input of the attention block
+        MB_TRY(make_linear_lnin(h, p + "0.mha.in_proj_weight", p + "0.mha.in_proj_bias", 3 * D, D, ln_in, &L.qkv));
+        MB_TRY(make_linear_res(h, p + "0.mha.out_proj.weight", p + "0.mha.out_proj.bias", D, D, ln_in, &L.out));     // + x_l (bert.py:139)
+        MB_TRY(make_linear_lnin(h, p + "1.net.0.weight", p + "1.net.0.bias", c.mlp_dim, D, L.ln1, &L.up));
+        MB_TRY(make_linear_res(h, p + "1.net.2.weight", p + "1.net.2.bias", D, c.mlp_dim, L.ln1, &L.down));          // + LN1(y1) (bert.py:70)
+    }
+    const LNW& ln_last = c.depth > 0 ? h->layers[c.depth - 1].ln2 : h->ln_first;
+    MB_TRY(make_linear_lnin(h, "last_layer.0.weight", "last_layer.0.bias", D, D, ln_last, &h->head));
+    MB_TRY(make_linear_lnin(h, "prediction_layer.weight", "prediction_layer.bias", c.codebook_splits * h->V, D, h->ln_head, &h->pred));
     // buffers of the reference module that carry no information for this path
     auto it = h->staged[MB_GENERATOR].find("bits_to_indices");
     if (it != h->staged[MB_GENERATOR].end()) { cudaFree(it->second.ptr); h->staged[MB_GENERATOR].erase(it); }
@@ -460,7 +519,9 @@ static int set_gemm_attr() {
 template <int BN>
 static int set_gemm_attr_bn() {
     MB_TRY((set_gemm_attr<BN, 0>())); MB_TRY((set_gemm_attr<BN, 1>())); MB_TRY((set_gemm_attr<BN, 2>()));
-    MB_TRY((set_gemm_attr<BN, 3>())); MB_TRY((set_gemm_attr<BN, 4>()));
+    MB_TRY((set_gemm_attr<BN, 3>())); MB_TRY((set_gemm_attr<BN, 4>())); MB_TRY((set_gemm_attr<BN, 5>()));
+    MB_TRY((set_gemm_attr<BN, 6>())); MB_TRY((set_gemm_attr<BN, 7>())); MB_TRY((set_gemm_attr<BN, 8>()));
+    MB_TRY((set_gemm_attr<BN, 9>()));
     return 0;
 }
 static int init_kernel_attrs() {
@@ -497,6 +558,11 @@ static int launch_gemm_bn(mb_handle* h, const CUtensorMap& ta, const CUtensorMap
         case 2: gemm_bf16_tcgen05_kernel<BN, 2><<<grid, 384, smem, st>>>(ta, tb, p); break;
         case 3: gemm_bf16_tcgen05_kernel<BN, 3><<<grid, 384, smem, st>>>(ta, tb, p); break;
         case 4: gemm_bf16_tcgen05_kernel<BN, 4><<<grid, 384, smem, st>>>(ta, tb, p); break;
+        case 5: gemm_bf16_tcgen05_kernel<BN, 5><<<grid, 384, smem, st>>>(ta, tb, p); break;
+        case 6: gemm_bf16_tcgen05_kernel<BN, 6><<<grid, 384, smem, st>>>(ta, tb, p); break;
+        case 7: gemm_bf16_tcgen05_kernel<BN, 7><<<grid, 384, smem, st>>>(ta, tb, p); break;
+        case 8: gemm_bf16_tcgen05_kernel<BN, 8><<<grid, 384, smem, st>>>(ta, tb, p); break;
+        case 9: gemm_bf16_tcgen05_kernel<BN, 9><<<grid, 384, smem, st>>>(ta, tb, p); break;
         default: return fail(MB_ERR_INVALID, "bad epilogue %d", epi);
     }
     CU_TRY(cudaGetLastError());
@@ -506,17 +572,20 @@ static int launch_gemm_bn(mb_handle* h, const CUtensorMap& ta, const CUtensorMap
 static int launch_gemm(mb_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, int BN, const GemmParams& p, int epi,
                        int num_sms, cudaStream_t st) {
     if (p.K % 64 || p.N % BN) return fail(MB_ERR_INVALID, "gemm shape M=%d N=%d K=%d BN=%d", p.M, p.N, p.K, BN);
+    if ((epi == EPI_RES_LN_BF16_STATS || epi == EPI_LNIN_GELU_BF16_STATS) && (BN != 256 || p.N != 256 * (LN_PARTIALS / 2)))
+        return fail(MB_ERR_INVALID, "row-statistics epilogue needs N=%d, BN=256 (got N=%d BN=%d)", 256 * (LN_PARTIALS / 2), p.N, BN);
     if (BN == 256) return launch_gemm_bn<256>(h, ta, tb, p, epi, num_sms, st);
     if (BN == 128) return launch_gemm_bn<128>(h, ta, tb, p, epi, num_sms, st);
     if (BN == 64) return launch_gemm_bn<64>(h, ta, tb, p, epi, num_sms, st);
     return fail(MB_ERR_INVALID, "bad BN %d", BN);
 }
 static int run_linear(mb_handle* h, int kind, const CUtensorMap& ta, const Linear& L, int M, int epi, const __nv_bfloat16* residual,
-                      void* out, int ldo, cudaStream_t st, int seq_in = 0, int seq_out = 0) {
+                      const float2* stats_in, float2* stats_out, void* out, int ldo, cudaStream_t st, int seq_in = 0, int seq_out = 0) {
     ProfScope prof(h, kind, st);
     GemmParams p;
-    p.M = M; p.N = L.N; p.K = L.K; p.bias = L.b; p.residual = residual; p.ldr = L.N; p.out = out; p.ldo = ldo;
-    p.seq_in = seq_in; p.seq_out = seq_out;
+    p.M = M; p.N = L.N; p.K = L.K; p.bias = L.b; p.vec2 = L.v2; p.residual = residual; p.ldr = L.N;
+    p.stats_in = stats_in; p.stats_out = stats_out; p.inv_d = 1.0f / (float)h->cfg.hidden_dim; p.eps = 1e-12f;
+    p.out = out; p.ldo = ldo; p.seq_in = seq_in; p.seq_out = seq_out;
     return launch_gemm(h, ta, L.tm, L.BN, p, epi, h->num_sms, st);
 }
 
@@ -527,15 +596,21 @@ static int ensure_ws(mb_handle* h, int n_seq) {
     free_ws(h);
     const size_t rows = (((size_t)n_seq * h->S + 127) / 128) * 128;
     const int D = h->cfg.hidden_dim;
-    MB_TRY(dev_alloc(h, &h->x, rows * D, false));
+    MB_TRY(dev_alloc(h, &h->yA, rows * D, false));
+    MB_TRY(dev_alloc(h, &h->yB, rows * D, false));
     MB_TRY(dev_alloc(h, &h->qkv, rows * 3 * D, false));
     MB_TRY(dev_alloc(h, &h->att, rows * D, false));
     MB_TRY(dev_alloc(h, &h->hmid, rows * h->cfg.mlp_dim, false));
-    MB_TRY(dev_alloc(h, &h->pre, rows * D, false));
-    CU_TRY(cudaMemset(h->x, 0, rows * D * 2));
+    MB_TRY(dev_alloc(h, &h->stA, rows * LN_PARTIALS, false));
+    MB_TRY(dev_alloc(h, &h->stB, rows * LN_PARTIALS, false));
+    // rows beyond n_seq*S only ever feed accumulator rows that are never stored; keep them finite
+    CU_TRY(cudaMemset(h->yA, 0, rows * D * 2));
+    CU_TRY(cudaMemset(h->yB, 0, rows * D * 2));
+    CU_TRY(cudaMemset(h->qkv, 0, rows * 3 * D * 2));
     CU_TRY(cudaMemset(h->att, 0, rows * D * 2));
     CU_TRY(cudaMemset(h->hmid, 0, rows * h->cfg.mlp_dim * 2));
-    MB_TRY(make_tmap_bf16(&h->tm_x, h->x, rows, D, 128));
+    MB_TRY(make_tmap_bf16(&h->tm_yA, h->yA, rows, D, 128));
+    MB_TRY(make_tmap_bf16(&h->tm_yB, h->yB, rows, D, 128));
     MB_TRY(make_tmap_bf16(&h->tm_att, h->att, rows, D, 128));
     MB_TRY(make_tmap_bf16(&h->tm_hmid, h->hmid, rows, h->cfg.mlp_dim, 128));
     MB_TRY(make_tmap_bf16(&h->tm_qkv_big, h->qkv, rows, 3 * D, 256));
@@ -574,33 +649,27 @@ static int forward_impl(mb_handle* h, const int64_t* tokens, int n_token_rows, c
     const mb_config& c = h->cfg;
     constexpr int D = 1024;
     const int M = n_seq * h->S;
-    const float eps = 1e-12f;
-    const int rows_per_blk = 8;
-    const unsigned ln_grid = (unsigned)((M + rows_per_blk - 1) / rows_per_blk);
-    { ProfScope prof(h, MB_PROF_EMBED, st);
-    embed_ln_kernel<D><<<ln_grid, 256, 0, st>>>(tokens, n_token_rows, labels, n_label_rows, drop, n_seq, c.seq_len, c.codebook_splits,
-                                                 h->eff_bits, c.nclass, h->w_in_t, h->b_in, h->class_emb, h->pos, h->ln_first.g,
-                                                 h->ln_first.b, eps, h->x); }
+    // y0 = input_proj(bits) | class_emb, + pos_emb  (pre-LayerNorm; first_layer's LN is folded into layer 0)
+    {
+        ProfScope prof(h, MB_PROF_EMBED, st);
+        embed_kernel<D><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(tokens, n_token_rows, labels, n_label_rows, drop, n_seq, c.seq_len,
+                                                                  c.codebook_splits, h->eff_bits, c.nclass, h->w_in_t, h->b_in,
+                                                                  h->class_emb, h->pos, h->yA, h->stA, LN_PARTIALS);
+    }
     CU_TRY(cudaGetLastError()); h->launches++;
     for (int l = 0; l < c.depth; ++l) {
         const Layer& L = h->layers[l];
-        MB_TRY(run_linear(h, MB_PROF_GEMM_QKV, h->tm_x, L.qkv, M, EPI_BIAS_BF16, nullptr, h->qkv, 3 * D, st));
+        // attention block (bert.py:137-139): yB = out_proj(MHA(LN(yA))) + LN(yA)
+        MB_TRY(run_linear(h, MB_PROF_GEMM_QKV, h->tm_yA, L.qkv, M, EPI_LNIN_BF16, nullptr, h->stA, nullptr, h->qkv, 3 * D, st));
         MB_TRY(run_attention(h, h->tm_qkv_big, h->tm_qkv_row, h->qkv, h->att, n_seq, h->S, D, c.heads, h->num_sms, st));
-        MB_TRY(run_linear(h, MB_PROF_GEMM_OUT, h->tm_att, L.out, M, EPI_BIAS_RES_F32, h->x, h->pre, D, st));
-        { ProfScope prof(h, MB_PROF_LAYERNORM, st);
-        layernorm_kernel<D><<<ln_grid, 256, 0, st>>>(h->pre, L.ln1.g, L.ln1.b, eps, h->x, M); }
-        CU_TRY(cudaGetLastError()); h->launches++;
-        MB_TRY(run_linear(h, MB_PROF_GEMM_UP, h->tm_x, L.up, M, EPI_BIAS_GELU_BF16, nullptr, h->hmid, c.mlp_dim, st));
-        MB_TRY(run_linear(h, MB_PROF_GEMM_DOWN, h->tm_hmid, L.down, M, EPI_BIAS_RES_F32, h->x, h->pre, D, st));
-        { ProfScope prof(h, MB_PROF_LAYERNORM, st);
-        layernorm_kernel<D><<<ln_grid, 256, 0, st>>>(h->pre, L.ln2.g, L.ln2.b, eps, h->x, M); }
-        CU_TRY(cudaGetLastError()); h->launches++;
+        MB_TRY(run_linear(h, MB_PROF_GEMM_OUT, h->tm_att, L.out, M, EPI_RES_LN_BF16_STATS, h->yA, h->stA, h->stB, h->yB, D, st));
+        // feed-forward block (bert.py:69-70): yA = W2 gelu(W1 LN1(yB) + b1) + b2 + LN1(yB)
+        MB_TRY(run_linear(h, MB_PROF_GEMM_UP, h->tm_yB, L.up, M, EPI_LNIN_GELU_BF16, nullptr, h->stB, nullptr, h->hmid, c.mlp_dim, st));
+        MB_TRY(run_linear(h, MB_PROF_GEMM_DOWN, h->tm_hmid, L.down, M, EPI_RES_LN_BF16_STATS, h->yB, h->stB, h->stA, h->yA, D, st));
     }
-    MB_TRY(run_linear(h, MB_PROF_GEMM_HEAD, h->tm_x, h->head, M, 4 /*bias+gelu -> f32*/, nullptr, h->pre, D, st));
-    { ProfScope prof(h, MB_PROF_LAYERNORM, st);
-    layernorm_kernel<D><<<ln_grid, 256, 0, st>>>(h->pre, h->ln_head.g, h->ln_head.b, eps, h->att, M); }
-    CU_TRY(cudaGetLastError()); h->launches++;
-    MB_TRY(run_linear(h, MB_PROF_GEMM_HEAD, h->tm_att, h->pred, M, EPI_BIAS_F32_SEQ, nullptr, logits, h->pred.N, st, h->S, c.seq_len));
+    // head (bert.py:500-503): LN(gelu(W LN2(yA) + b)) -> prediction layer, class-token row dropped
+    MB_TRY(run_linear(h, MB_PROF_GEMM_HEAD, h->tm_yA, h->head, M, EPI_LNIN_GELU_BF16_STATS, nullptr, h->stA, h->stB, h->yB, D, st));
+    MB_TRY(run_linear(h, MB_PROF_GEMM_HEAD, h->tm_yB, h->pred, M, EPI_LNIN_F32_SEQ, nullptr, h->stB, nullptr, logits, h->pred.N, st, h->S, c.seq_len));
     return 0;
 }
 
@@ -829,8 +898,9 @@ static int test_num_sms() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     return n;
 }
-extern "C" int mb_test_gemm(const uint16_t* A, const uint16_t* W, const float* bias, const uint16_t* residual, void* out, int M,
-                            int N, int K, int epi, int seq_in, int seq_out, mb_stream stream) {
+extern "C" int mb_test_gemm_ex(const uint16_t* A, const uint16_t* W, const float* bias, const float* vec2, const uint16_t* residual,
+                               const float* stats_in, float* stats_out, void* out, int M, int N, int K, int epi, int seq_in,
+                               int seq_out, float inv_d, float eps, mb_stream stream) {
     MB_TRY(init_kernel_attrs());
     const int BN = pick_bn(N);
     if (!BN) return fail(MB_ERR_INVALID, "N=%d not tileable", N);
@@ -838,9 +908,14 @@ extern "C" int mb_test_gemm(const uint16_t* A, const uint16_t* W, const float* b
     MB_TRY(make_tmap_bf16(&ta, A, M, K, 128));
     MB_TRY(make_tmap_bf16(&tb, W, N, K, BN));
     GemmParams p;
-    p.M = M; p.N = N; p.K = K; p.bias = bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = N;
-    p.out = out; p.ldo = N; p.seq_in = seq_in; p.seq_out = seq_out;
+    p.M = M; p.N = N; p.K = K; p.bias = bias; p.vec2 = vec2; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = N;
+    p.stats_in = reinterpret_cast<const float2*>(stats_in); p.stats_out = reinterpret_cast<float2*>(stats_out);
+    p.inv_d = inv_d; p.eps = eps; p.out = out; p.ldo = N; p.seq_in = seq_in; p.seq_out = seq_out;
     return launch_gemm(nullptr, ta, tb, BN, p, epi, test_num_sms(), (cudaStream_t)stream);
+}
+extern "C" int mb_test_gemm(const uint16_t* A, const uint16_t* W, const float* bias, const uint16_t* residual, void* out, int M,
+                            int N, int K, int epi, int seq_in, int seq_out, mb_stream stream) {
+    return mb_test_gemm_ex(A, W, bias, nullptr, residual, nullptr, nullptr, out, M, N, K, epi, seq_in, seq_out, 0.f, 0.f, stream);
 }
 extern "C" int mb_test_attention(const uint16_t* qkv, uint16_t* out, int n_seq, int S, int D, int H, mb_stream stream) {
     MB_TRY(init_kernel_attrs());
@@ -850,11 +925,4 @@ extern "C" int mb_test_attention(const uint16_t* qkv, uint16_t* out, int n_seq, 
     MB_TRY(make_tmap_bf16(&tr, qkv, (uint64_t)n_seq * S, 3 * D, 16));
     return run_attention(nullptr, tb, tr, reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out),
                          n_seq, S, D, H, test_num_sms(), (cudaStream_t)stream);
-}
-extern "C" int mb_test_layernorm(const float* in, const float* gamma, const float* beta, float eps, uint16_t* out, int rows, int D,
-                                 mb_stream stream) {
-    if (D != 1024) return fail(MB_ERR_INVALID, "layernorm is built for D=1024");
-    layernorm_kernel<1024><<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(in, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(out), rows);
-    CU_TRY(cudaGetLastError());
-    return 0;
 }

@@ -1,36 +1,55 @@
-// Persistent warp-specialised bf16 GEMM for sm_100a:  out[M,N] = epilogue(A[M,K] * W[N,K]^T + bias)
+// Persistent warp-specialised bf16 GEMM for sm_100a:  out[M,N] = epilogue(A[M,K] * W[N,K]^T)
 //
 //   A, W     bf16, K contiguous ("K-major"), loaded by TMA (128B swizzle) into a STAGES-deep smem ring
 //   MMA      tcgen05.mma.cta_group::1.kind::f16, M=128 x N=BN x K=16, fp32 accumulators in TMEM,
 //            two accumulator stages (2*BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1
 //   roles    warp 0 lane 0: TMA producer | warp 1 lane 0: MMA issuer | warp 2: TMEM alloc/dealloc
-//            warps 4..11: epilogue (warp%4 = TMEM lane quarter, (warp-4)/4 = column half)
+//            warps 4..11: epilogue (warp%4 = TMEM lane quarter, (warp-4)/4 = column half), one thread per output row
 //   tiles    static round-robin over (m_blk, n_blk) with n fastest, so CTAs resident at the same time share A rows
 //            in L2 and the weight matrix (<= 8 MB) stays L2-resident for the whole launch.
 //
-// This is the kernel behind every Linear of the reference's LFQBert (bert.py:26-31,84,411-417): QKV in-proj,
-// attention out-proj, MLP up (+GELU) / down, head (+GELU) and the prediction layer.
+// This is the kernel behind every Linear of the reference's LFQBert (bert.py:26-31,84,411-417).
+//
+// LayerNorm never runs as a kernel of its own.  The residual stream is kept as the PRE-norm sum y (bf16) plus per-row
+// partial (sum, sum of squares) statistics, and the reference's post-norm structure  x = LN(y) ; out = Linear(x)  is
+// evaluated as
+//     Linear(LN(y))[m,n] = rstd_m * (sum_k y[m,k] W'[n,k]  -  mean_m * u[n]) + c[n]
+//     W' = W * gamma (folded, bf16),  u[n] = sum_k W'[n,k],  c[n] = sum_k W[n,k] beta[k] + b[n]           ("LN-in" epilogues)
+// and wherever the reference adds the residual x, the epilogue rebuilds x = (y - mean) * rstd * gamma + beta from y and the
+// row statistics ("residual" epilogue), writes the new pre-norm sum as bf16 and emits its partial statistics.
+// eps = 1e-12 as in the reference (bert.py:33,86,394,414).
 #pragma once
 #include "ptx.cuh"
 
 namespace mb {
 
 enum EpiMode : int {
-    EPI_BIAS_BF16 = 0,       // out bf16 = acc + bias
-    EPI_BIAS_GELU_BF16 = 1,  // out bf16 = gelu_erf(acc + bias)
-    EPI_BIAS_RES_F32 = 2,    // out fp32 = acc + bias + residual(bf16)         (pre-LayerNorm sum)
-    EPI_BIAS_F32_SEQ = 3,    // out fp32 = acc + bias, rows remapped: drop row seq_in-1 of every sequence (bert.py:503)
-    EPI_BIAS_GELU_F32 = 4,   // out fp32 = gelu_erf(acc + bias)                  (head, before its LayerNorm)
+    EPI_BIAS_BF16 = 0,            // out bf16 = acc + bias
+    EPI_BIAS_GELU_BF16 = 1,       // out bf16 = gelu_erf(acc + bias)
+    EPI_BIAS_RES_F32 = 2,         // out fp32 = acc + bias + residual(bf16)
+    EPI_BIAS_F32_SEQ = 3,         // out fp32 = acc + bias, rows remapped: drop row seq_in-1 of every sequence (bert.py:503)
+    EPI_BIAS_GELU_F32 = 4,        // out fp32 = gelu_erf(acc + bias)
+    EPI_LNIN_BF16 = 5,            // out bf16 = rstd*(acc - mean*u) + c                               (QKV in-proj)
+    EPI_LNIN_GELU_BF16 = 6,       // out bf16 = gelu_erf(rstd*(acc - mean*u) + c)                     (MLP up)
+    EPI_RES_LN_BF16_STATS = 7,    // out bf16 = acc + bias + LN(y_res)  (+ partial row stats)         (attention out-proj, MLP down)
+    EPI_LNIN_GELU_BF16_STATS = 8, // out bf16 = gelu_erf(rstd*(acc - mean*u) + c) (+ partial stats)   (head last_layer.0)
+    EPI_LNIN_F32_SEQ = 9,         // out fp32 = rstd*(acc - mean*u) + c, class row dropped            (prediction layer)
 };
+constexpr int GEMM_NUM_EPI = 10;
+constexpr int LN_PARTIALS = 8;    // partial (sum, sumsq) slots per row: one per (256-wide n-block, 128-column half) of a 1024-wide row
 
 struct GemmParams {
     int M, N, K;
-    const float* bias;               // [N]
-    const __nv_bfloat16* residual;   // [M, ldr] for EPI_BIAS_RES_F32
+    const float* bias;               // [N]: bias | c (LN-in) | bias + beta (residual)
+    const float* vec2;               // [N]: u (LN-in) | gamma (residual)
+    const __nv_bfloat16* residual;   // [M, ldr]: residual (mode 2) | pre-norm y of the residual stream (mode 7)
     int ldr;
+    const float2* stats_in;          // [M][LN_PARTIALS] partial (sum, sumsq) of the LayerNorm input rows (A rows or y_res rows)
+    float2* stats_out;               // [M][LN_PARTIALS] partials of the rows written by this GEMM (STATS modes; N == 1024, BN == 256)
+    float inv_d, eps;                // 1 / normalised width, LayerNorm eps
     void* out;                       // bf16 or fp32, row stride ldo elements
     int ldo;
-    int seq_in, seq_out;             // EPI_BIAS_F32_SEQ: rows per sequence in A / kept rows per sequence in out
+    int seq_in, seq_out;             // *_SEQ: rows per sequence in A / kept rows per sequence in out
 };
 
 template <int BN>
@@ -60,11 +79,31 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return fmaf(-fabsf(x), h, fmaxf(x, 0.f));      // x > 0: x - x h ; x < 0: x h
 }
 
+// mean and rstd of a row from its LN_PARTIALS partial sums
+__device__ __forceinline__ void ln_row_stats(const float2* __restrict__ st, float inv_d, float eps, float& mean, float& rstd) {
+    const float4* q = reinterpret_cast<const float4*>(st);
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_PARTIALS / 2; ++i) {
+        const float4 v = __ldg(q + i);
+        s += v.x + v.z; ss += v.y + v.w;
+    }
+    mean = s * inv_d;
+    const float var = fmaxf(fmaf(-mean, mean, ss * inv_d), 0.f);
+    rstd = rsqrtf(var + eps);
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(384, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, GemmParams p) {
     using C = GemmCfg<BN>;
     constexpr int BM = C::BM, BK = C::BK, STAGES = C::STAGES;
+    constexpr bool kLnIn = EPI == EPI_LNIN_BF16 || EPI == EPI_LNIN_GELU_BF16 || EPI == EPI_LNIN_GELU_BF16_STATS || EPI == EPI_LNIN_F32_SEQ;
+    constexpr bool kGelu = EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_F32 || EPI == EPI_LNIN_GELU_BF16 || EPI == EPI_LNIN_GELU_BF16_STATS;
+    constexpr bool kStats = EPI == EPI_RES_LN_BF16_STATS || EPI == EPI_LNIN_GELU_BF16_STATS;
+    constexpr bool kSeq = EPI == EPI_BIAS_F32_SEQ || EPI == EPI_LNIN_F32_SEQ;
+    constexpr bool kOutBf16 = EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_LNIN_BF16 || EPI == EPI_LNIN_GELU_BF16 ||
+                              EPI == EPI_RES_LN_BF16_STATS || EPI == EPI_LNIN_GELU_BF16_STATS;
     extern __shared__ uint8_t smem_raw[];
     // 128B-swizzle atoms are 1024 B: align the ring manually (dynamic smem base is only guaranteed 16 B aligned)
     const uint32_t raw = smem_u32(smem_raw);
@@ -141,17 +180,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int m_blk = tile / num_n, n_blk = tile % num_n;
             const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-            mbar_wait(&tmem_full[as], aphase);
-            tc_fence_after();
             const int row = m_blk * BM + quarter * 32 + lane;
             const bool row_ok = row < p.M;
             long long out_row = row;
             bool store_ok = row_ok;
-            if (EPI == EPI_BIAS_F32_SEQ) {
+            if (kSeq) {
                 const int sq = row / p.seq_in, r = row - sq * p.seq_in;
                 store_ok = row_ok && r < p.seq_out;
                 out_row = (long long)sq * p.seq_out + r;
             }
+            // LayerNorm row statistics (of the A row for LN-in modes, of the residual-stream row for the residual mode):
+            // fetched before the accumulator wait so the loads overlap the tile's MMAs
+            float rs = 1.f, nmr = 0.f;              // rstd, -mean * rstd
+            if ((kLnIn || EPI == EPI_RES_LN_BF16_STATS) && row_ok) {
+                float mean, rstd;
+                ln_row_stats(p.stats_in + (size_t)row * LN_PARTIALS, p.inv_d, p.eps, mean, rstd);
+                rs = rstd; nmr = -mean * rstd;
+            }
+            float st_sum = 0.f, st_sq = 0.f;
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
 #pragma unroll 1
             for (int c = 0; c < COLS_PER_WARP; c += 32) {
                 const int col0 = half * COLS_PER_WARP + c;
@@ -163,50 +211,73 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-                    f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
-                    f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-                    f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
-                    f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+                    if (kLnIn) {   // rstd*acc + (-mean*rstd)*u + c
+                        const float4 u4 = __ldg(reinterpret_cast<const float4*>(p.vec2 + n0 + j));
+                        f[j + 0] = fmaf(rs, __uint_as_float(v[j + 0]), fmaf(nmr, u4.x, b4.x));
+                        f[j + 1] = fmaf(rs, __uint_as_float(v[j + 1]), fmaf(nmr, u4.y, b4.y));
+                        f[j + 2] = fmaf(rs, __uint_as_float(v[j + 2]), fmaf(nmr, u4.z, b4.z));
+                        f[j + 3] = fmaf(rs, __uint_as_float(v[j + 3]), fmaf(nmr, u4.w, b4.w));
+                    } else {
+                        f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
+                        f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+                        f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+                        f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+                    }
                 }
-                if (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_F32) {
+                if (kGelu) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
                 }
-                if (EPI == EPI_BIAS_RES_F32) {
+                if (EPI == EPI_BIAS_RES_F32 || EPI == EPI_RES_LN_BF16_STATS) {
                     if (row_ok) {
                         const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + n0);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const uint4 r4 = __ldg(rp + j);
                             const uint32_t w[4] = {r4.x, r4.y, r4.z, r4.w};
+                            if (EPI == EPI_RES_LN_BF16_STATS) {   // + ((y - mean) * rstd) * gamma   (beta is folded into p.bias)
+                                const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.vec2 + n0 + j * 8));
+                                const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.vec2 + n0 + j * 8 + 4));
+                                const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                f[j * 8 + 2 * t + 0] += __uint_as_float(w[t] << 16);
-                                f[j * 8 + 2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
+                                for (int t = 0; t < 4; ++t) {
+                                    f[j * 8 + 2 * t + 0] = fmaf(fmaf(__uint_as_float(w[t] << 16), rs, nmr), g[2 * t], f[j * 8 + 2 * t + 0]);
+                                    f[j * 8 + 2 * t + 1] = fmaf(fmaf(__uint_as_float(w[t] & 0xffff0000u), rs, nmr), g[2 * t + 1], f[j * 8 + 2 * t + 1]);
+                                }
+                            } else {
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    f[j * 8 + 2 * t + 0] += __uint_as_float(w[t] << 16);
+                                    f[j * 8 + 2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
+                                }
                             }
                         }
                     }
                 }
-                if (store_ok) {
-                    if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
+                if (kOutBf16) {
+                    uint32_t w[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                        w[j] = *reinterpret_cast<uint32_t*>(&h);
+                        if (kStats) {   // statistics of the values as stored (bf16-rounded): the consumer normalises those
+                            const float a = __uint_as_float(w[j] << 16), b = __uint_as_float(w[j] & 0xffff0000u);
+                            st_sum += a + b;
+                            st_sq = fmaf(a, a, fmaf(b, b, st_sq));
+                        }
+                    }
+                    if (store_ok) {
                         uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (size_t)out_row * p.ldo + n0);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint32_t w[4];
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                __nv_bfloat162 h = __floats2bfloat162_rn(f[j * 8 + 2 * t], f[j * 8 + 2 * t + 1]);
-                                w[t] = *reinterpret_cast<uint32_t*>(&h);
-                            }
-                            op[j] = make_uint4(w[0], w[1], w[2], w[3]);
-                        }
-                    } else {
-                        float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + (size_t)out_row * p.ldo + n0);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        for (int j = 0; j < 4; ++j) op[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
                     }
+                } else if (store_ok) {
+                    float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + (size_t)out_row * p.ldo + n0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
                 }
             }
+            if (kStats && row_ok) p.stats_out[(size_t)row * LN_PARTIALS + n_blk * 2 + half] = make_float2(st_sum, st_sq);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);

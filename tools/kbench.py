@@ -51,26 +51,25 @@ def main():
         A = torch.randn((M, K), device="cuda", generator=g).to(torch.bfloat16)
         W = (torch.randn((N, K), device="cuda", generator=g) * 0.03).to(torch.bfloat16)
         bias = torch.randn((N,), device="cuda", generator=g)
-        res = torch.randn((M, N), device="cuda", generator=g).to(torch.bfloat16) if epi == 2 else None
-        out = torch.empty((M, N), dtype=torch.bfloat16 if epi in (0, 1) else torch.float32, device="cuda")
-        ms = timeit(lambda: _lib.check(L.mb_test_gemm(p(A), p(W), p(bias), p(res), p(out), M, N, K, epi, 0, 0, st)), a.iters, flush)
+        vec2 = torch.randn((N,), device="cuda", generator=g)
+        res = torch.randn((M, N), device="cuda", generator=g).to(torch.bfloat16) if epi == 7 else None
+        stats = torch.rand((M, 8, 2), device="cuda", generator=g) + 1.0
+        stats[:, :, 1] += 40.0
+        sto = torch.empty((M, 8, 2), device="cuda") if epi in (7, 8) else None
+        out = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+        ms = timeit(lambda: _lib.check(L.mb_test_gemm_ex(p(A), p(W), p(bias), p(vec2), p(res), p(stats), p(sto), p(out), M, N, K, epi, 0, 0,
+                                                         1.0 / 1024, 1e-12, st)), a.iters, flush)
         rows.append((name, ms, 2.0 * M * N * K / ms / 1e9, "TFLOP/s"))
 
-    gemm("gemm_qkv  N3072 K1024 bias->bf16", 3072, 1024, 0)
-    gemm("gemm_out  N1024 K1024 bias+res->f32", 1024, 1024, 2)
-    gemm("gemm_up   N4096 K1024 bias+gelu->bf16", 4096, 1024, 1)
-    gemm("gemm_down N1024 K4096 bias+res->f32", 1024, 4096, 2)
+    gemm("gemm_qkv  N3072 K1024 LN-in->bf16", 3072, 1024, 5)
+    gemm("gemm_out  N1024 K1024 +LN(res)->bf16+stats", 1024, 1024, 7)
+    gemm("gemm_up   N4096 K1024 LN-in+gelu->bf16", 4096, 1024, 6)
+    gemm("gemm_down N1024 K4096 +LN(res)->bf16+stats", 1024, 4096, 7)
     if not a.only or a.only in "attention":
         qkv = torch.randn((M, 3072), device="cuda", generator=g).to(torch.bfloat16)
         out = torch.empty((M, 1024), dtype=torch.bfloat16, device="cuda")
         ms = timeit(lambda: _lib.check(L.mb_test_attention(p(qkv), p(out), a.seqs, 257, 1024, 16, st)), a.iters, flush)
         rows.append(("attention S257 H16 d64", ms, 4.0 * 257 * 257 * 64 * 16 * a.seqs / ms / 1e9, "TFLOP/s"))
-    if not a.only or a.only in "layernorm":
-        x = torch.randn((M, 1024), device="cuda", generator=g)
-        gm = torch.randn((1024,), device="cuda", generator=g)
-        out = torch.empty((M, 1024), dtype=torch.bfloat16, device="cuda")
-        ms = timeit(lambda: _lib.check(L.mb_test_layernorm(p(x), p(gm), p(gm), 1e-12, p(out), M, 1024, st)), a.iters, flush)
-        rows.append(("layernorm f32->bf16", ms, M * 1024 * 6 / ms / 1e6, "GB/s"))
     for name, ms, rate, unit in rows:
         print(f"{name:42s} {ms:8.4f} ms  {rate:9.1f} {unit}")
 
