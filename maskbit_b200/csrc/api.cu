@@ -78,6 +78,9 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t rows, uint6
     return 0;
 }
 
+// bf16 row-major [rows, cols] output map for the GEMM epilogue's TMA stores: box = 64 columns x 32 rows
+static int make_tmap_out(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols) { return make_tmap_bf16(tm, ptr, rows, cols, 32); }
+
 // ------------------------------------------------------------------------------------------------ small kernels
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -161,7 +164,9 @@ struct DevTensor { float* ptr = nullptr; std::vector<int64_t> shape; size_t nume
 
 // b / v2 follow GemmParams::bias / vec2: plain (bias, -), LN-in (c, u), residual (bias + beta_res, gamma_res)
 struct Linear {
-    __nv_bfloat16* w = nullptr; float* b = nullptr; float* v2 = nullptr; int N = 0, K = 0, BN = 0; CUtensorMap tm;
+    __nv_bfloat16* w = nullptr; float* b = nullptr; float* v2 = nullptr; int N = 0, K = 0, BN = 0;
+    CUtensorMap tm;        // box BN rows (1-CTA kernel)
+    CUtensorMap tm_half;   // box 128 rows (CTA-pair kernel), valid when BN == 256
 };
 struct LNW { float* g = nullptr; float* b = nullptr; };
 struct Layer { Linear qkv, out, up, down; LNW ln1, ln2; };
@@ -189,6 +194,7 @@ struct mb_handle {
     __nv_bfloat16 *yA = nullptr, *yB = nullptr, *qkv = nullptr, *att = nullptr, *hmid = nullptr;
     float2 *stA = nullptr, *stB = nullptr;
     CUtensorMap tm_yA, tm_yB, tm_att, tm_hmid, tm_qkv_big, tm_qkv_row;
+    CUtensorMap tmo_yA, tmo_yB, tmo_qkv, tmo_hmid;   // output maps (box 64 x 32) of the same buffers
     // sampler workspace
     int cap_sample_B = 0;
     int64_t *tok_a = nullptr, *tok_b = nullptr, *pred_buf = nullptr, *combined = nullptr;
@@ -362,6 +368,7 @@ static int make_linear_lnin(mb_handle* h, const std::string& wname, const std::s
     fold_ln_kernel<<<N, 256>>>(w.ptr, ln.g, ln.b, b.ptr, L->w, L->v2, L->b, K);
     CU_TRY(cudaGetLastError());
     MB_TRY(make_tmap_bf16(&L->tm, L->w, N, K, L->BN));
+    if (L->BN == 256) MB_TRY(make_tmap_bf16(&L->tm_half, L->w, N, K, 128));
     CU_TRY(cudaDeviceSynchronize());
     cudaFree(w.ptr); cudaFree(b.ptr);
     h->staged[MB_GENERATOR].erase(wname); h->staged[MB_GENERATOR].erase(bname);
@@ -381,6 +388,7 @@ static int make_linear_res(mb_handle* h, const std::string& wname, const std::st
     add_vec_kernel<<<(N + 255) / 256, 256>>>(b.ptr, ln_res.b, L->b, N);
     CU_TRY(cudaGetLastError());
     MB_TRY(make_tmap_bf16(&L->tm, L->w, N, K, L->BN));
+    MB_TRY(make_tmap_bf16(&L->tm_half, L->w, N, K, 128));
     CU_TRY(cudaDeviceSynchronize());
     cudaFree(w.ptr); cudaFree(b.ptr);
     h->staged[MB_GENERATOR].erase(wname); h->staged[MB_GENERATOR].erase(bname);
@@ -524,10 +532,21 @@ static int set_gemm_attr_bn() {
     MB_TRY((set_gemm_attr<BN, 9>()));
     return 0;
 }
+template <int EPI>
+static int set_gemm2_attr() {
+    CU_TRY(cudaFuncSetAttribute(gemm2_bf16_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES));
+    return 0;
+}
+// CTA-pair (cta_group::2) GEMM for every N % 256 == 0 Linear; MASKBIT_B200_GEMM_2CTA=0 selects the 1-CTA kernel (A/B timing)
+static bool g_use_2cta = true;
 static int init_kernel_attrs() {
     static bool done = false;
     if (done) return 0;
+    if (const char* e = getenv("MASKBIT_B200_GEMM_2CTA")) g_use_2cta = atoi(e) != 0;
     MB_TRY(set_gemm_attr_bn<64>()); MB_TRY(set_gemm_attr_bn<128>()); MB_TRY(set_gemm_attr_bn<256>());
+    MB_TRY(set_gemm2_attr<0>()); MB_TRY(set_gemm2_attr<1>()); MB_TRY(set_gemm2_attr<2>()); MB_TRY(set_gemm2_attr<3>());
+    MB_TRY(set_gemm2_attr<4>()); MB_TRY(set_gemm2_attr<5>()); MB_TRY(set_gemm2_attr<6>()); MB_TRY(set_gemm2_attr<7>());
+    MB_TRY(set_gemm2_attr<8>()); MB_TRY(set_gemm2_attr<9>());
     CU_TRY(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ATT_MAXS * ATT_LDS * 2));
     CU_TRY(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_BYTES));
@@ -569,8 +588,38 @@ static int launch_gemm_bn(mb_handle* h, const CUtensorMap& ta, const CUtensorMap
     if (h) h->launches++;
     return 0;
 }
-static int launch_gemm(mb_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, int BN, const GemmParams& p, int epi,
-                       int num_sms, cudaStream_t st) {
+static int launch_gemm2(mb_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
+                        int epi, int num_sms, cudaStream_t st) {
+    const int tiles = ((p.M + 255) / 256) * (p.N / 256);
+    int pairs = num_sms / 2;
+    if (tiles < pairs) pairs = tiles;
+    const int grid = 2 * pairs, smem = Gemm2Cfg::SMEM_BYTES;
+    switch (epi) {
+        case 0: gemm2_bf16_tcgen05_kernel<0><<<grid, 384, smem, st>>>(ta, tb, tc, p); break;
+        case 1: gemm2_bf16_tcgen05_kernel<1><<<grid, 384, smem, st>>>(ta, tb, tc, p); break;
+        case 2: gemm2_bf16_tcgen05_kernel<2><<<grid, 384, smem, st>>>(ta, tb, tc, p); break;
+        case 3: gemm2_bf16_tcgen05_kernel<3><<<grid, 384, smem, st>>>(ta, tb, tc, p); break;
+        case 4: gemm2_bf16_tcgen05_kernel<4><<<grid, 384, smem, st>>>(ta, tb, tc, p); break;
+        case 5: gemm2_bf16_tcgen05_kernel<5><<<grid, 384, smem, st>>>(ta, tb, tc, p); break;
+        case 6: gemm2_bf16_tcgen05_kernel<6><<<grid, 384, smem, st>>>(ta, tb, tc, p); break;
+        case 7: gemm2_bf16_tcgen05_kernel<7><<<grid, 384, smem, st>>>(ta, tb, tc, p); break;
+        case 8: gemm2_bf16_tcgen05_kernel<8><<<grid, 384, smem, st>>>(ta, tb, tc, p); break;
+        case 9: gemm2_bf16_tcgen05_kernel<9><<<grid, 384, smem, st>>>(ta, tb, tc, p); break;
+        default: return fail(MB_ERR_INVALID, "bad epilogue %d", epi);
+    }
+    CU_TRY(cudaGetLastError());
+    if (h) h->launches++;
+    return 0;
+}
+// tb_half: the weight's tensor map with a 128-row box (CTA-pair kernel: each CTA stages half of the 256-row B tile)
+// tc: output tensor map (box 64 x 32) for the bf16-output epilogues of the CTA-pair kernel
+static int launch_gemm(mb_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tb_half, const CUtensorMap* tc,
+                       int BN, const GemmParams& p, int epi, int num_sms, cudaStream_t st) {
+    if (g_use_2cta && tb_half && (tc || !gemm2_tma_store(epi)) && BN == 256 && p.K % 64 == 0 && p.N % 256 == 0 && num_sms >= 2) {
+        if ((epi == EPI_RES_LN_BF16_STATS || epi == EPI_LNIN_GELU_BF16_STATS) && p.N != 256 * (LN_PARTIALS / 2))
+            return fail(MB_ERR_INVALID, "row-statistics epilogue needs N=%d (got N=%d)", 256 * (LN_PARTIALS / 2), p.N);
+        return launch_gemm2(h, ta, *tb_half, tc ? *tc : ta, p, epi, num_sms, st);
+    }
     if (p.K % 64 || p.N % BN) return fail(MB_ERR_INVALID, "gemm shape M=%d N=%d K=%d BN=%d", p.M, p.N, p.K, BN);
     if ((epi == EPI_RES_LN_BF16_STATS || epi == EPI_LNIN_GELU_BF16_STATS) && (BN != 256 || p.N != 256 * (LN_PARTIALS / 2)))
         return fail(MB_ERR_INVALID, "row-statistics epilogue needs N=%d, BN=256 (got N=%d BN=%d)", 256 * (LN_PARTIALS / 2), p.N, BN);
@@ -580,13 +629,14 @@ static int launch_gemm(mb_handle* h, const CUtensorMap& ta, const CUtensorMap& t
     return fail(MB_ERR_INVALID, "bad BN %d", BN);
 }
 static int run_linear(mb_handle* h, int kind, const CUtensorMap& ta, const Linear& L, int M, int epi, const __nv_bfloat16* residual,
-                      const float2* stats_in, float2* stats_out, void* out, int ldo, cudaStream_t st, int seq_in = 0, int seq_out = 0) {
+                      const float2* stats_in, float2* stats_out, void* out, const CUtensorMap* tm_out, int ldo, cudaStream_t st,
+                      int seq_in = 0, int seq_out = 0) {
     ProfScope prof(h, kind, st);
     GemmParams p;
     p.M = M; p.N = L.N; p.K = L.K; p.bias = L.b; p.vec2 = L.v2; p.residual = residual; p.ldr = L.N;
     p.stats_in = stats_in; p.stats_out = stats_out; p.inv_d = 1.0f / (float)h->cfg.hidden_dim; p.eps = 1e-12f;
     p.out = out; p.ldo = ldo; p.seq_in = seq_in; p.seq_out = seq_out;
-    return launch_gemm(h, ta, L.tm, L.BN, p, epi, h->num_sms, st);
+    return launch_gemm(h, ta, L.tm, L.BN == 256 ? &L.tm_half : nullptr, tm_out, L.BN, p, epi, h->num_sms, st);
 }
 
 // ------------------------------------------------------------------------------------------------ generator forward
@@ -615,6 +665,10 @@ static int ensure_ws(mb_handle* h, int n_seq) {
     MB_TRY(make_tmap_bf16(&h->tm_hmid, h->hmid, rows, h->cfg.mlp_dim, 128));
     MB_TRY(make_tmap_bf16(&h->tm_qkv_big, h->qkv, rows, 3 * D, 256));
     MB_TRY(make_tmap_bf16(&h->tm_qkv_row, h->qkv, rows, 3 * D, 16));
+    MB_TRY(make_tmap_out(&h->tmo_yA, h->yA, rows, D));
+    MB_TRY(make_tmap_out(&h->tmo_yB, h->yB, rows, D));
+    MB_TRY(make_tmap_out(&h->tmo_qkv, h->qkv, rows, 3 * D));
+    MB_TRY(make_tmap_out(&h->tmo_hmid, h->hmid, rows, h->cfg.mlp_dim));
     h->cap_seqs = n_seq; h->cap_rows = rows;
     return 0;
 }
@@ -660,16 +714,16 @@ static int forward_impl(mb_handle* h, const int64_t* tokens, int n_token_rows, c
     for (int l = 0; l < c.depth; ++l) {
         const Layer& L = h->layers[l];
         // attention block (bert.py:137-139): yB = out_proj(MHA(LN(yA))) + LN(yA)
-        MB_TRY(run_linear(h, MB_PROF_GEMM_QKV, h->tm_yA, L.qkv, M, EPI_LNIN_BF16, nullptr, h->stA, nullptr, h->qkv, 3 * D, st));
+        MB_TRY(run_linear(h, MB_PROF_GEMM_QKV, h->tm_yA, L.qkv, M, EPI_LNIN_BF16, nullptr, h->stA, nullptr, h->qkv, &h->tmo_qkv, 3 * D, st));
         MB_TRY(run_attention(h, h->tm_qkv_big, h->tm_qkv_row, h->qkv, h->att, n_seq, h->S, D, c.heads, h->num_sms, st));
-        MB_TRY(run_linear(h, MB_PROF_GEMM_OUT, h->tm_att, L.out, M, EPI_RES_LN_BF16_STATS, h->yA, h->stA, h->stB, h->yB, D, st));
+        MB_TRY(run_linear(h, MB_PROF_GEMM_OUT, h->tm_att, L.out, M, EPI_RES_LN_BF16_STATS, h->yA, h->stA, h->stB, h->yB, &h->tmo_yB, D, st));
         // feed-forward block (bert.py:69-70): yA = W2 gelu(W1 LN1(yB) + b1) + b2 + LN1(yB)
-        MB_TRY(run_linear(h, MB_PROF_GEMM_UP, h->tm_yB, L.up, M, EPI_LNIN_GELU_BF16, nullptr, h->stB, nullptr, h->hmid, c.mlp_dim, st));
-        MB_TRY(run_linear(h, MB_PROF_GEMM_DOWN, h->tm_hmid, L.down, M, EPI_RES_LN_BF16_STATS, h->yB, h->stB, h->stA, h->yA, D, st));
+        MB_TRY(run_linear(h, MB_PROF_GEMM_UP, h->tm_yB, L.up, M, EPI_LNIN_GELU_BF16, nullptr, h->stB, nullptr, h->hmid, &h->tmo_hmid, c.mlp_dim, st));
+        MB_TRY(run_linear(h, MB_PROF_GEMM_DOWN, h->tm_hmid, L.down, M, EPI_RES_LN_BF16_STATS, h->yB, h->stB, h->stA, h->yA, &h->tmo_yA, D, st));
     }
     // head (bert.py:500-503): LN(gelu(W LN2(yA) + b)) -> prediction layer, class-token row dropped
-    MB_TRY(run_linear(h, MB_PROF_GEMM_HEAD, h->tm_yA, h->head, M, EPI_LNIN_GELU_BF16_STATS, nullptr, h->stA, h->stB, h->yB, D, st));
-    MB_TRY(run_linear(h, MB_PROF_GEMM_HEAD, h->tm_yB, h->pred, M, EPI_LNIN_F32_SEQ, nullptr, h->stB, nullptr, logits, h->pred.N, st, h->S, c.seq_len));
+    MB_TRY(run_linear(h, MB_PROF_GEMM_HEAD, h->tm_yA, h->head, M, EPI_LNIN_GELU_BF16_STATS, nullptr, h->stA, h->stB, h->yB, &h->tmo_yB, D, st));
+    MB_TRY(run_linear(h, MB_PROF_GEMM_HEAD, h->tm_yB, h->pred, M, EPI_LNIN_F32_SEQ, nullptr, h->stB, nullptr, logits, nullptr, h->pred.N, st, h->S, c.seq_len));
     return 0;
 }
 
@@ -904,14 +958,18 @@ extern "C" int mb_test_gemm_ex(const uint16_t* A, const uint16_t* W, const float
     MB_TRY(init_kernel_attrs());
     const int BN = pick_bn(N);
     if (!BN) return fail(MB_ERR_INVALID, "N=%d not tileable", N);
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, tbh, tc;
     MB_TRY(make_tmap_bf16(&ta, A, M, K, 128));
     MB_TRY(make_tmap_bf16(&tb, W, N, K, BN));
+    if (BN == 256) MB_TRY(make_tmap_bf16(&tbh, W, N, K, 128));
+    const bool bf16_out = gemm2_tma_store(epi);
+    if (BN == 256 && bf16_out) MB_TRY(make_tmap_out(&tc, out, M, N));
     GemmParams p;
     p.M = M; p.N = N; p.K = K; p.bias = bias; p.vec2 = vec2; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = N;
     p.stats_in = reinterpret_cast<const float2*>(stats_in); p.stats_out = reinterpret_cast<float2*>(stats_out);
     p.inv_d = inv_d; p.eps = eps; p.out = out; p.ldo = N; p.seq_in = seq_in; p.seq_out = seq_out;
-    return launch_gemm(nullptr, ta, tb, BN, p, epi, test_num_sms(), (cudaStream_t)stream);
+    return launch_gemm(nullptr, ta, tb, BN == 256 ? &tbh : nullptr, (BN == 256 && bf16_out) ? &tc : nullptr, BN, p, epi, test_num_sms(),
+                       (cudaStream_t)stream);
 }
 extern "C" int mb_test_gemm(const uint16_t* A, const uint16_t* W, const float* bias, const uint16_t* residual, void* out, int M,
                             int N, int K, int epi, int seq_in, int seq_out, mb_stream stream) {

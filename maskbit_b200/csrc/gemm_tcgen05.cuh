@@ -21,6 +21,13 @@
 #pragma once
 #include "ptx.cuh"
 
+#ifndef GEMM_TIMING_NO_STORE
+#define GEMM_TIMING_NO_STORE 0   // timing experiments only: skip the bf16 output stores
+#endif
+#ifndef GEMM_TIMING_NO_GELU
+#define GEMM_TIMING_NO_GELU 0    // timing experiments only
+#endif
+
 namespace mb {
 
 enum EpiMode : int {
@@ -79,6 +86,43 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return fmaf(-fabsf(x), h, fmaxf(x, 0.f));      // x > 0: x - x h ; x < 0: x h
 }
 
+// Two GELUs at once on packed fp32 pairs (FFMA2 / FMUL2): 10 FMA-pipe + 4 ALU + 4 MUFU issue slots per pair instead of 2 x 16.
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+    const float a0 = fabsf(x0), a1 = fabsf(x1);
+    float d0, d1, t0, t1, e0, e1, q0, q1, s0, s1, h0, h1;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\tmov.b64 rc, {%5, %5};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(0.3275911f * 0.70710678118654752f), "f"(1.0f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+    // q = ((((a5 t + a4) t + a3) t + a2) t + a1) * 0.5, Horner on pairs
+    asm("{\n\t.reg .b64 rt, rq, rk;\n\t"
+        "mov.b64 rt, {%2, %3};\n\t"
+        "mov.b64 rq, {%4, %4};\n\tmov.b64 rk, {%5, %5};\n\tfma.rn.f32x2 rq, rq, rt, rk;\n\t"
+        "mov.b64 rk, {%6, %6};\n\tfma.rn.f32x2 rq, rq, rt, rk;\n\t"
+        "mov.b64 rk, {%7, %7};\n\tfma.rn.f32x2 rq, rq, rt, rk;\n\t"
+        "mov.b64 rk, {%8, %8};\n\tfma.rn.f32x2 rq, rq, rt, rk;\n\t"
+        "mul.rn.f32x2 rq, rq, rt;\n\t"
+        "mov.b64 {%0, %1}, rq;\n\t}"
+        : "=f"(q0), "=f"(q1)
+        : "f"(t0), "f"(t1), "f"(0.5f * 1.061405429f), "f"(0.5f * -1.453152027f), "f"(0.5f * 1.421413741f),
+          "f"(0.5f * -0.284496736f), "f"(0.5f * 0.254829592f));
+    asm("{\n\t.reg .b64 rx, rc, rd;\n\t"
+        "mov.b64 rx, {%2, %3};\n\tmov.b64 rc, {%4, %4};\n\t"
+        "mul.rn.f32x2 rd, rx, rx;\n\tmul.rn.f32x2 rd, rd, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(s0), "=f"(s1) : "f"(x0), "f"(x1), "f"(-0.72134752044448170f));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(s0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(s1));
+    const float r0 = fmaxf(x0, 0.f), r1 = fmaxf(x1, 0.f);
+    // h = q * e ; out = relu(x) - |x| * h
+    asm("{\n\t.reg .b64 rq, re, ra, rr, rd;\n\t"
+        "mov.b64 rq, {%2, %3};\n\tmov.b64 re, {%4, %5};\n\tmov.b64 ra, {%6, %7};\n\tmov.b64 rr, {%8, %9};\n\t"
+        "mul.rn.f32x2 rd, rq, re;\n\tfma.rn.f32x2 rd, ra, rd, rr;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(h0), "=f"(h1) : "f"(q0), "f"(q1), "f"(e0), "f"(e1), "f"(-a0), "f"(-a1), "f"(r0), "f"(r1));
+    x0 = h0; x1 = h1;
+}
+
 // mean and rstd of a row from its LN_PARTIALS partial sums
 __device__ __forceinline__ void ln_row_stats(const float2* __restrict__ st, float inv_d, float eps, float& mean, float& rstd) {
     const float4* q = reinterpret_cast<const float4*>(st);
@@ -93,17 +137,159 @@ __device__ __forceinline__ void ln_row_stats(const float2* __restrict__ st, floa
     rstd = rsqrtf(var + eps);
 }
 
+// One output row per thread.  epi_prepare runs before the accumulator wait (its loads overlap the tile's MMAs), epi_run after.
+struct EpiRow { int row; bool row_ok, store_ok; long long out_row; float rs, nmr; };
+
+template <int EPI>
+__device__ __forceinline__ EpiRow epi_prepare(const GemmParams& p, int row) {
+    constexpr bool kLnIn = EPI == EPI_LNIN_BF16 || EPI == EPI_LNIN_GELU_BF16 || EPI == EPI_LNIN_GELU_BF16_STATS || EPI == EPI_LNIN_F32_SEQ;
+    constexpr bool kSeq = EPI == EPI_BIAS_F32_SEQ || EPI == EPI_LNIN_F32_SEQ;
+    EpiRow r;
+    r.row = row; r.row_ok = row < p.M; r.out_row = row; r.store_ok = r.row_ok;
+    if (kSeq) {
+        const int sq = row / p.seq_in, rr = row - sq * p.seq_in;
+        r.store_ok = r.row_ok && rr < p.seq_out;
+        r.out_row = (long long)sq * p.seq_out + rr;
+    }
+    // LayerNorm row statistics: of the A row for LN-in modes, of the residual-stream row for the residual mode
+    r.rs = 1.f; r.nmr = 0.f;                // rstd, -mean * rstd
+    if ((kLnIn || EPI == EPI_RES_LN_BF16_STATS) && r.row_ok) {
+        float mean, rstd;
+        ln_row_stats(p.stats_in + (size_t)row * LN_PARTIALS, p.inv_d, p.eps, mean, rstd);
+        r.rs = rstd; r.nmr = -mean * rstd;
+    }
+    return r;
+}
+
+// Output staging for the TMA-store path: the warp's 32 rows x 64 bf16 columns as 128-byte rows with the 128B swizzle
+// (what a box {64, 32} store with CU_TENSOR_MAP_SWIZZLE_128B reads).  Direct per-thread stores write 16 B of a different
+// row per lane and instruction -- half-sector L2 writes that cap the K=1024 GEMMs at ~70 % of their store-free speed.
+struct EpiStage {
+    uint8_t* buf;             // 4 KB, 1024-byte aligned, private to the warp
+    const CUtensorMap* tm;    // output tensor map, box {64 columns, 32 rows}
+    int row0;                 // first output row of the warp's 32-row slab
+};
+
+// taddr: TMEM address of this warp's lane quarter at column 0 of the accumulator tile; the warp handles columns
+// [half * BN/2, (half+1) * BN/2) of the BN-wide tile n_blk.  kTma: bf16 output through smem + cp.async.bulk.tensor store.
+template <int BN, int EPI, bool kTma = false>
+__device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, uint32_t taddr, int n_blk, int half,
+                                        EpiStage stg = EpiStage{nullptr, nullptr, 0}) {
+    constexpr bool kLnIn = EPI == EPI_LNIN_BF16 || EPI == EPI_LNIN_GELU_BF16 || EPI == EPI_LNIN_GELU_BF16_STATS || EPI == EPI_LNIN_F32_SEQ;
+    constexpr bool kGelu = EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_F32 || EPI == EPI_LNIN_GELU_BF16 || EPI == EPI_LNIN_GELU_BF16_STATS;
+    constexpr bool kStats = EPI == EPI_RES_LN_BF16_STATS || EPI == EPI_LNIN_GELU_BF16_STATS;
+    constexpr bool kOutBf16 = EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_LNIN_BF16 || EPI == EPI_LNIN_GELU_BF16 ||
+                              EPI == EPI_RES_LN_BF16_STATS || EPI == EPI_LNIN_GELU_BF16_STATS;
+    constexpr int COLS_PER_WARP = BN / 2;
+    const int row = er.row;
+    const bool row_ok = er.row_ok, store_ok = er.store_ok;
+    const long long out_row = er.out_row;
+    const float rs = er.rs, nmr = er.nmr;
+    float st_sum = 0.f, st_sq = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < COLS_PER_WARP; c += 32) {
+        const int col0 = half * COLS_PER_WARP + c;
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + col0, v);
+        tmem_ld_wait();
+        const int n0 = n_blk * BN + col0;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+            if (kLnIn) {   // rstd*acc + (-mean*rstd)*u + c
+                const float4 u4 = __ldg(reinterpret_cast<const float4*>(p.vec2 + n0 + j));
+                f[j + 0] = fmaf(rs, __uint_as_float(v[j + 0]), fmaf(nmr, u4.x, b4.x));
+                f[j + 1] = fmaf(rs, __uint_as_float(v[j + 1]), fmaf(nmr, u4.y, b4.y));
+                f[j + 2] = fmaf(rs, __uint_as_float(v[j + 2]), fmaf(nmr, u4.z, b4.z));
+                f[j + 3] = fmaf(rs, __uint_as_float(v[j + 3]), fmaf(nmr, u4.w, b4.w));
+            } else {
+                f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
+                f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+                f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+                f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+            }
+        }
+        if (kGelu && !GEMM_TIMING_NO_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) gelu_erf2(f[j], f[j + 1]);
+        }
+        if (EPI == EPI_BIAS_RES_F32 || EPI == EPI_RES_LN_BF16_STATS) {
+            if (row_ok) {
+                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + n0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint4 r4 = __ldg(rp + j);
+                    const uint32_t w[4] = {r4.x, r4.y, r4.z, r4.w};
+                    if (EPI == EPI_RES_LN_BF16_STATS) {   // + ((y - mean) * rstd) * gamma   (beta is folded into p.bias)
+                        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.vec2 + n0 + j * 8));
+                        const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.vec2 + n0 + j * 8 + 4));
+                        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            f[j * 8 + 2 * t + 0] = fmaf(fmaf(__uint_as_float(w[t] << 16), rs, nmr), g[2 * t], f[j * 8 + 2 * t + 0]);
+                            f[j * 8 + 2 * t + 1] = fmaf(fmaf(__uint_as_float(w[t] & 0xffff0000u), rs, nmr), g[2 * t + 1], f[j * 8 + 2 * t + 1]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            f[j * 8 + 2 * t + 0] += __uint_as_float(w[t] << 16);
+                            f[j * 8 + 2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
+                        }
+                    }
+                }
+            }
+        }
+        if (kOutBf16) {
+            uint32_t w[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                w[j] = *reinterpret_cast<uint32_t*>(&h);
+                if (kStats) {   // statistics of the values as stored (bf16-rounded): the consumer normalises those
+                    const float a = __uint_as_float(w[j] << 16), b = __uint_as_float(w[j] & 0xffff0000u);
+                    st_sum += a + b;
+                    st_sq = fmaf(a, a, fmaf(b, b, st_sq));
+                }
+            }
+            if (kTma) {
+                const int lane = threadIdx.x & 31;
+                const int sub = (c >> 5) & 1;                 // which 32-column half of the 64-column staging row
+                if (sub == 0) {                               // the previous store must have finished reading the buffer
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+                }
+                uint8_t* rowp = stg.buf + lane * 128;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(rowp + (((sub * 4 + j) ^ (lane & 7)) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+                if (sub == 1) {
+                    fence_async_proxy();                      // generic-proxy smem writes -> visible to the bulk copy
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(stg.tm, stg.buf, n0 - 32, stg.row0);
+                        tma_store_commit();
+                    }
+                }
+            } else if (store_ok && !GEMM_TIMING_NO_STORE) {
+                uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (size_t)out_row * p.ldo + n0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) op[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+            }
+        } else if (store_ok) {
+            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + (size_t)out_row * p.ldo + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        }
+    }
+    if (kStats && row_ok) p.stats_out[(size_t)row * LN_PARTIALS + n_blk * 2 + half] = make_float2(st_sum, st_sq);
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(384, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, GemmParams p) {
     using C = GemmCfg<BN>;
     constexpr int BM = C::BM, BK = C::BK, STAGES = C::STAGES;
-    constexpr bool kLnIn = EPI == EPI_LNIN_BF16 || EPI == EPI_LNIN_GELU_BF16 || EPI == EPI_LNIN_GELU_BF16_STATS || EPI == EPI_LNIN_F32_SEQ;
-    constexpr bool kGelu = EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_F32 || EPI == EPI_LNIN_GELU_BF16 || EPI == EPI_LNIN_GELU_BF16_STATS;
-    constexpr bool kStats = EPI == EPI_RES_LN_BF16_STATS || EPI == EPI_LNIN_GELU_BF16_STATS;
-    constexpr bool kSeq = EPI == EPI_BIAS_F32_SEQ || EPI == EPI_LNIN_F32_SEQ;
-    constexpr bool kOutBf16 = EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_LNIN_BF16 || EPI == EPI_LNIN_GELU_BF16 ||
-                              EPI == EPI_RES_LN_BF16_STATS || EPI == EPI_LNIN_GELU_BF16_STATS;
     extern __shared__ uint8_t smem_raw[];
     // 128B-swizzle atoms are 1024 B: align the ring manually (dynamic smem base is only guaranteed 16 B aligned)
     const uint32_t raw = smem_u32(smem_raw);
@@ -175,109 +361,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         }
     } else if (warp >= 4) {  // ---------------- epilogue: TMEM -> registers -> global
         const int quarter = warp & 3, half = (warp - 4) >> 2;
-        constexpr int COLS_PER_WARP = BN / 2;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int m_blk = tile / num_n, n_blk = tile % num_n;
             const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-            const int row = m_blk * BM + quarter * 32 + lane;
-            const bool row_ok = row < p.M;
-            long long out_row = row;
-            bool store_ok = row_ok;
-            if (kSeq) {
-                const int sq = row / p.seq_in, r = row - sq * p.seq_in;
-                store_ok = row_ok && r < p.seq_out;
-                out_row = (long long)sq * p.seq_out + r;
-            }
-            // LayerNorm row statistics (of the A row for LN-in modes, of the residual-stream row for the residual mode):
-            // fetched before the accumulator wait so the loads overlap the tile's MMAs
-            float rs = 1.f, nmr = 0.f;              // rstd, -mean * rstd
-            if ((kLnIn || EPI == EPI_RES_LN_BF16_STATS) && row_ok) {
-                float mean, rstd;
-                ln_row_stats(p.stats_in + (size_t)row * LN_PARTIALS, p.inv_d, p.eps, mean, rstd);
-                rs = rstd; nmr = -mean * rstd;
-            }
-            float st_sum = 0.f, st_sq = 0.f;
+            const EpiRow er = epi_prepare<EPI>(p, m_blk * BM + quarter * 32 + lane);
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < COLS_PER_WARP; c += 32) {
-                const int col0 = half * COLS_PER_WARP + c;
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + col0, v);
-                tmem_ld_wait();
-                const int n0 = n_blk * BN + col0;
-                float f[32];
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-                    if (kLnIn) {   // rstd*acc + (-mean*rstd)*u + c
-                        const float4 u4 = __ldg(reinterpret_cast<const float4*>(p.vec2 + n0 + j));
-                        f[j + 0] = fmaf(rs, __uint_as_float(v[j + 0]), fmaf(nmr, u4.x, b4.x));
-                        f[j + 1] = fmaf(rs, __uint_as_float(v[j + 1]), fmaf(nmr, u4.y, b4.y));
-                        f[j + 2] = fmaf(rs, __uint_as_float(v[j + 2]), fmaf(nmr, u4.z, b4.z));
-                        f[j + 3] = fmaf(rs, __uint_as_float(v[j + 3]), fmaf(nmr, u4.w, b4.w));
-                    } else {
-                        f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
-                        f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-                        f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
-                        f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
-                    }
-                }
-                if (kGelu) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-                }
-                if (EPI == EPI_BIAS_RES_F32 || EPI == EPI_RES_LN_BF16_STATS) {
-                    if (row_ok) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + n0);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint4 r4 = __ldg(rp + j);
-                            const uint32_t w[4] = {r4.x, r4.y, r4.z, r4.w};
-                            if (EPI == EPI_RES_LN_BF16_STATS) {   // + ((y - mean) * rstd) * gamma   (beta is folded into p.bias)
-                                const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.vec2 + n0 + j * 8));
-                                const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.vec2 + n0 + j * 8 + 4));
-                                const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-#pragma unroll
-                                for (int t = 0; t < 4; ++t) {
-                                    f[j * 8 + 2 * t + 0] = fmaf(fmaf(__uint_as_float(w[t] << 16), rs, nmr), g[2 * t], f[j * 8 + 2 * t + 0]);
-                                    f[j * 8 + 2 * t + 1] = fmaf(fmaf(__uint_as_float(w[t] & 0xffff0000u), rs, nmr), g[2 * t + 1], f[j * 8 + 2 * t + 1]);
-                                }
-                            } else {
-#pragma unroll
-                                for (int t = 0; t < 4; ++t) {
-                                    f[j * 8 + 2 * t + 0] += __uint_as_float(w[t] << 16);
-                                    f[j * 8 + 2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
-                                }
-                            }
-                        }
-                    }
-                }
-                if (kOutBf16) {
-                    uint32_t w[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                        w[j] = *reinterpret_cast<uint32_t*>(&h);
-                        if (kStats) {   // statistics of the values as stored (bf16-rounded): the consumer normalises those
-                            const float a = __uint_as_float(w[j] << 16), b = __uint_as_float(w[j] & 0xffff0000u);
-                            st_sum += a + b;
-                            st_sq = fmaf(a, a, fmaf(b, b, st_sq));
-                        }
-                    }
-                    if (store_ok) {
-                        uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (size_t)out_row * p.ldo + n0);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) op[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-                    }
-                } else if (store_ok) {
-                    float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + (size_t)out_row * p.ldo + n0);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                }
-            }
-            if (kStats && row_ok) p.stats_out[(size_t)row * LN_PARTIALS + n_blk * 2 + half] = make_float2(st_sum, st_sq);
+            epi_run<BN, EPI>(p, er, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN, n_blk, half);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -289,6 +380,137 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ CTA-pair variant
+// Same pipeline with tcgen05.mma.cta_group::2: a cluster of two CTAs (one TPC) computes a 256 x 256 tile, each CTA holding
+// the accumulators of its 128 rows in its own TMEM and staging only HALF of the B tile (128 of the 256 weight rows); the
+// tensor cores of both SMs read both halves.  Per CTA and k-block that is 16 KB of A + 16 KB of B instead of 16 + 32 KB:
+// a third less L2 -> SM traffic and shared-memory fill per MMA (the 1-CTA kernel is bound there, not in the tensor pipe),
+// which also makes room for 6 pipeline stages instead of 4.
+//   leader CTA (cluster rank 0): arms full[s] for the bytes of BOTH CTAs and issues every MMA;
+//   both CTAs: TMA producer for their own halves (completion signalled on the leader's full[s]), epilogue of their own rows;
+//   tcgen05.commit multicasts the "stage consumed" / "accumulator ready" arrivals to both CTAs; the epilogue warps of both
+//   CTAs release the accumulator stage on the leader's tmem_empty barrier.
+struct Gemm2Cfg {
+    static constexpr int BM = 256, BN = 256, BK = 64, STAGES = 6;
+    static constexpr int A_BYTES = 128 * BK * 2;      // per CTA
+    static constexpr int B_BYTES = 128 * BK * 2;      // per CTA (half of the 256 weight rows)
+    static constexpr int STG_BYTES = 8 * 4096;        // output staging: 8 epilogue warps x (32 rows x 128 B)
+    static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + STG_BYTES + 1024 + 256;
+};
+// bf16-output epilogues of the CTA-pair kernel go through shared memory and TMA stores
+__host__ __device__ constexpr bool gemm2_tma_store(int epi) {
+    return epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_LNIN_BF16 || epi == EPI_LNIN_GELU_BF16 ||
+           epi == EPI_RES_LN_BF16_STATS || epi == EPI_LNIN_GELU_BF16_STATS;
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                          const __grid_constant__ CUtensorMap tm_c, GemmParams p) {
+    using C = Gemm2Cfg;
+    constexpr int BN = C::BN, BK = C::BK, STAGES = C::STAGES;
+    constexpr bool kTma = gemm2_tma_store(EPI);
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* base = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    uint8_t* smem_a = base;
+    uint8_t* smem_b = base + STAGES * C::A_BYTES;
+    uint8_t* smem_stg = base + STAGES * (C::A_BYTES + C::B_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + C::STG_BYTES);
+    uint64_t* full = bars;                          // used in the leader CTA only
+    uint64_t* empty = bars + STAGES;                // per CTA, arrived by the leader's multicast commit
+    uint64_t* tmem_full = bars + 2 * STAGES;        // per CTA, arrived by the leader's multicast commit
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;   // leader only: 8 epilogue warps of each CTA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int num_m = (p.M + C::BM - 1) / C::BM, num_n = p.N / BN;
+    const int num_tiles = num_m * num_n, num_k = p.K / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_a);
+        tma_prefetch_desc(&tm_b);
+        if (kTma) tma_prefetch_desc(&tm_c);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 16); }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc_2sm<512>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();                              // barriers of both CTAs initialised before any remote arrive
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---------------- TMA producer (each CTA: its 128 A rows, its 128 of the 256 B rows)
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                const int m_blk = tile / num_n, n_blk = tile % num_n;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (C::A_BYTES + C::B_BYTES));
+                    const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
+                    tma_load_2d_2sm(smem_a + stage * C::A_BYTES, &tm_a, bar, kb * BK, m_blk * C::BM + (int)rank * 128);
+                    tma_load_2d_2sm(smem_b + stage * C::B_BYTES, &tm_b, bar, kb * BK, n_blk * BN + (int)rank * 128);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {  // ---------------- MMA issuer (leader CTA only)
+            constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, 256, BN);
+            int stage = 0; uint32_t phase = 0; uint32_t it = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+                const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t a_desc = make_sdesc_k128(smem_u32(smem_a + stage * C::A_BYTES));
+                    const uint64_t b_desc = make_sdesc_k128(smem_u32(smem_b + stage * C::B_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_f16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit_2sm(&empty[stage], 3);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_2sm(&tmem_full[as], 3);
+            }
+        }
+    } else if (warp >= 4) {  // ---------------- epilogue: each CTA its own 128 rows
+        const int quarter = warp & 3, half = (warp - 4) >> 2;
+        uint32_t it = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+            const int m_blk = tile / num_n, n_blk = tile % num_n;
+            const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+            const int row0 = m_blk * C::BM + (int)rank * 128 + quarter * 32;
+            const EpiRow er = epi_prepare<EPI>(p, row0 + lane);
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
+            epi_run<BN, EPI, kTma>(p, er, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN, n_blk, half,
+                                   EpiStage{smem_stg + (warp - 4) * 4096, &tm_c, row0});
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0));
+        }
+        if (kTma && lane == 0) tma_store_wait_all<0>();   // bulk stores complete before the CTA retires its smem
+    }
+    __syncwarp();
+    tc_fence_before();
+    cluster_sync_all();                              // the leader's MMAs write the peer's TMEM: both done before dealloc
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm<512>(tmem_base);
     }
 }
 
