@@ -163,6 +163,7 @@ def run_b200(args):
     import torch.distributed as dist
     from maskbit_b200 import build_models, load_config, sample, sampler_kwargs
     from maskbit_b200.masking import step_tables
+    from maskbit_b200.sharding import gather_images, rank_seed, shard_labels
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -183,19 +184,18 @@ def run_b200(args):
     B, T = args.batch, args.sampling_steps
     # global labels drawn once, sliced contiguously per rank (SURVEY.md 8d config 3 rule)
     all_labels = torch.randint(0, 1000, (world * B,), generator=torch.Generator().manual_seed(1234))
-    labels_host = all_labels[rank * B:(rank + 1) * B].contiguous().pin_memory()
+    labels_host = shard_labels(all_labels, rank, world).contiguous().pin_memory()
     labels_dev = labels_host.to(dev)
-    gathered = torch.empty((world * B, 256, 256, 3), dtype=torch.uint8, device=dev) if world > 1 else None
     out_host = torch.empty((B, 256, 256, 3), dtype=torch.uint8).pin_memory()
 
     def one_step(i, e2e):
         lab = labels_host.to(dev, non_blocking=True) if e2e else labels_dev
-        img, _ = sample(gen, tokenizer, num_samples=B, labels=lab, noise="device", seed=1000 + i, return_trace=False,
+        img, _ = sample(gen, tokenizer, num_samples=B, labels=lab, noise="device", seed=rank_seed(1000 + i, rank), return_trace=False,
                         skip_zero_scale_uncond=args.skip_dead_uncond, **kw)
         if e2e or world > 1:
             u8 = tokenizer.postprocess_uint8(img)
             if world > 1:
-                dist.all_gather_into_tensor(gathered, u8)      # the one collective: finished images (north_star)
+                gather_images(u8, world * B)                   # the one collective: finished images (north_star)
             if e2e:
                 out_host.copy_(u8, non_blocking=True)
         return img
