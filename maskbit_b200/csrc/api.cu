@@ -15,6 +15,7 @@
 #include "../../include/maskbit_b200.h"
 #include "attention.cuh"
 #include "attention_tc.cuh"
+#include "conv_tcgen05.cuh"
 #include "decoder.cuh"
 #include "embed_ln.cuh"
 #include "gemm_tcgen05.cuh"
@@ -75,6 +76,24 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t rows, uint6
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(MB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu", (int)r,
                                        (unsigned long long)rows, (unsigned long long)cols);
+    return 0;
+}
+
+// generic tiled map (innermost dimension first)
+static int make_tmap_nd(CUtensorMap* tm, CUtensorMapDataType dt, int elem_bytes, int rank, const void* ptr, const uint64_t* dims,
+                        const uint32_t* box) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(MB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t d[5], strides[4]; cuuint32_t b[5], estr[5];
+    uint64_t stride = elem_bytes;
+    for (int i = 0; i < rank; ++i) {
+        d[i] = dims[i]; b[i] = box[i]; estr[i] = 1;
+        stride *= dims[i];
+        if (i < rank - 1) strides[i] = stride;
+    }
+    CUresult r = fn(tm, dt, rank, const_cast<void*>(ptr), d, strides, b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MB_ERR_CUDA, "cuTensorMapEncodeTiled (rank %d) failed (%d)", rank, (int)r);
     return 0;
 }
 
@@ -170,7 +189,10 @@ struct Linear {
 };
 struct LNW { float* g = nullptr; float* b = nullptr; };
 struct Layer { Linear qkv, out, up, down; LNW ln1, ln2; };
-struct ConvW { __nv_bfloat16* hi = nullptr; __nv_bfloat16* lo = nullptr; float* bias = nullptr; int cin = 0, cout = 0, taps = 0; };
+struct ConvW {
+    __nv_bfloat16* hi = nullptr; __nv_bfloat16* lo = nullptr; float* bias = nullptr; int cin = 0, cout = 0, taps = 0;
+    CUtensorMap tm_hi, tm_lo;   // [cout][taps*cin], box 64 x 128
+};
 struct GNW { float* g = nullptr; float* b = nullptr; int C = 0; };
 struct ResBlockW { GNW n1, n2; ConvW c1, c2, nin; bool has_nin = false; };
 struct StageW { std::vector<ResBlockW> blocks; bool has_up = false; ConvW up; };
@@ -208,6 +230,8 @@ struct mb_handle {
     int dec_cap = 0;
     float *dx = nullptr, *dt1 = nullptr, *dt2 = nullptr, *gn_scale = nullptr, *gn_shift = nullptr;
     double2* gn_partial = nullptr;
+    __nv_bfloat16 *act_hi = nullptr, *act_lo = nullptr;   // zero-bordered bf16 hi / lo split of the current conv input
+    std::map<std::vector<uint64_t>, CUtensorMap> tmap_cache;   // activation / output maps keyed by (pointer, shape, box)
     // per-kernel-class CUDA-event timing (mb_profile_*): pairs of events recorded around launches on the launch stream
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -280,9 +304,10 @@ static void free_sample_ws(mb_handle* h) {
     h->tok_a = h->tok_b = h->pred_buf = h->combined = nullptr; h->logits_ws = nullptr; h->drop_ws = nullptr; h->cap_sample_B = 0;
 }
 static void free_dec_ws(mb_handle* h) {
-    void* ps[] = {h->dx, h->dt1, h->dt2, h->gn_scale, h->gn_shift, h->gn_partial};
+    void* ps[] = {h->dx, h->dt1, h->dt2, h->gn_scale, h->gn_shift, h->gn_partial, h->act_hi, h->act_lo};
     for (void* p : ps) if (p) cudaFree(p);
-    h->dx = h->dt1 = h->dt2 = h->gn_scale = h->gn_shift = nullptr; h->gn_partial = nullptr; h->dec_cap = 0;
+    h->dx = h->dt1 = h->dt2 = h->gn_scale = h->gn_shift = nullptr; h->gn_partial = nullptr; h->act_hi = h->act_lo = nullptr;
+    h->tmap_cache.clear(); h->dec_cap = 0;
 }
 
 extern "C" void mb_destroy(mb_handle* h) {
@@ -445,12 +470,14 @@ static int make_conv(mb_handle* h, const std::string& name, int cout, int cin, i
     DevTensor t;
     MB_TRY(take(h, MB_TOKENIZER, name + ".weight", {cout, cin, k, k}, &t));
     W->cin = cin; W->cout = cout; W->taps = k * k;
-    if (cin % CV_BK || cout % CV_BN) return fail(MB_ERR_INVALID, "conv %s: channels %d->%d not tileable", name.c_str(), cin, cout);
+    if (cin % ConvTcCfg::BK || cout % ConvTcCfg::BN) return fail(MB_ERR_INVALID, "conv %s: channels %d->%d not tileable", name.c_str(), cin, cout);
     const size_t n = (size_t)cout * cin * k * k;
     MB_TRY(dev_alloc(h, &W->hi, n));
     MB_TRY(dev_alloc(h, &W->lo, n));
     pack_conv_kernel<<<(unsigned)((n + 255) / 256), 256>>>(t.ptr, W->hi, W->lo, cout, cin, k * k);
     CU_TRY(cudaDeviceSynchronize());
+    MB_TRY(make_tmap_bf16(&W->tm_hi, W->hi, cout, (uint64_t)k * k * cin, 128));
+    MB_TRY(make_tmap_bf16(&W->tm_lo, W->lo, cout, (uint64_t)k * k * cin, 128));
     cudaFree(t.ptr); h->staged[MB_TOKENIZER].erase(name + ".weight");
     if (bias) MB_TRY(keep_f32(h, MB_TOKENIZER, name + ".bias", {cout}, &W->bias));
     return 0;
@@ -549,7 +576,7 @@ static int init_kernel_attrs() {
     MB_TRY(set_gemm2_attr<8>()); MB_TRY(set_gemm2_attr<9>());
     CU_TRY(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ATT_MAXS * ATT_LDS * 2));
     CU_TRY(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES));
-    CU_TRY(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg::SMEM_BYTES));
     done = true;
     return 0;
 }
@@ -793,10 +820,24 @@ static int ensure_dec_ws(mb_handle* h, int nb) {
     MB_TRY(dev_alloc(h, &h->gn_scale, (size_t)nb * 1024, false));
     MB_TRY(dev_alloc(h, &h->gn_shift, (size_t)nb * 1024, false));
     MB_TRY(dev_alloc(h, &h->gn_partial, (size_t)nb * 64 * 32, false));
+    // padded split inputs: the largest (R+2)^2 * C over the conv inputs (an upsample conv reads its input at the output size)
+    size_t max_pad = 0;
+    {
+        int Rr = P;
+        for (size_t j = 0; j < h->ups.size(); ++j) {
+            for (auto& b : h->ups[j].blocks) {
+                const int cmax = b.c1.cin > b.c1.cout ? b.c1.cin : b.c1.cout;
+                const size_t e = (size_t)(Rr + 2) * (Rr + 2) * cmax; if (e > max_pad) max_pad = e;
+            }
+            if (h->ups[j].has_up) { Rr *= 2; const size_t e = (size_t)(Rr + 2) * (Rr + 2) * h->ups[j].up.cin; if (e > max_pad) max_pad = e; }
+        }
+        const size_t e0 = (size_t)(P + 2) * (P + 2) * h->dec_c0; if (e0 > max_pad) max_pad = e0;
+    }
+    MB_TRY(dev_alloc(h, &h->act_hi, max_pad * nb, false));
+    MB_TRY(dev_alloc(h, &h->act_lo, max_pad * nb, false));
     h->dec_cap = nb;
     return 0;
 }
-static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 static int run_gn(mb_handle* h, const float* x, const GNW& g, int nb, int R, cudaStream_t st) {
     const int HW = R * R;
@@ -808,17 +849,46 @@ static int run_gn(mb_handle* h, const float* x, const GNW& g, int nb, int R, cud
     CU_TRY(cudaGetLastError()); h->launches++;
     return 0;
 }
+static int cached_tmap(mb_handle* h, CUtensorMap** out, CUtensorMapDataType dt, int elem_bytes, int rank, const void* ptr,
+                       const uint64_t* dims, const uint32_t* box) {
+    std::vector<uint64_t> key = {(uint64_t)(uintptr_t)ptr, (uint64_t)dt, (uint64_t)rank};
+    for (int i = 0; i < rank; ++i) { key.push_back(dims[i]); key.push_back(box[i]); }
+    auto it = h->tmap_cache.find(key);
+    if (it == h->tmap_cache.end()) {
+        CUtensorMap tm;
+        MB_TRY(make_tmap_nd(&tm, dt, elem_bytes, rank, ptr, dims, box));
+        it = h->tmap_cache.emplace(key, tm).first;
+    }
+    *out = &it->second;
+    return 0;
+}
+// out = conv(act(in)) (+bias) (+residual): act = GroupNorm-apply + SiLU when gn, nearest x2 upsample when up (autoencoder.py:85-96,224-225)
 static int run_conv(mb_handle* h, const float* in, float* out, const ConvW& w, int nb, int R, bool gn, int up, const float* residual,
                     cudaStream_t st) {
-    ConvParams p;
-    p.in = in; p.out = out; p.w_hi = w.hi; p.w_lo = w.lo; p.bias = w.bias; p.residual = residual;
-    p.gn_scale = gn ? h->gn_scale : nullptr; p.gn_shift = gn ? h->gn_shift : nullptr;
-    p.B = nb; p.H = R; p.W = R; p.Cin = w.cin; p.Cout = w.cout; p.taps = w.taps; p.up = up; p.logW = ilog2(R); p.logH = ilog2(R);
-    if ((1 << p.logW) != R) return fail(MB_ERR_INVALID, "decoder resolution %d is not a power of two", R);
-    const long long npix = (long long)nb * R * R;
-    dim3 grid((unsigned)((npix + CV_BM - 1) / CV_BM), w.cout / CV_BN);
+    if (R < 16 || (R & (R - 1))) return fail(MB_ERR_INVALID, "decoder resolution %d unsupported (power of two >= 16)", R);
+    {
+        ProfScope prof(h, MB_PROF_DEC_IO, st);
+        const long long total = (long long)nb * (R + 2) * (R + 2) * (w.cin / 8);
+        act_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, gn ? h->gn_scale : nullptr, gn ? h->gn_shift : nullptr,
+                                                                          h->act_hi, h->act_lo, nb, R, R, w.cin, up);
+        CU_TRY(cudaGetLastError()); h->launches++;
+    }
+    ConvTcParams p;
+    p.n_img = nb; p.H = R; p.W = R; p.Cin = w.cin; p.Cout = w.cout; p.taps = w.taps;
+    p.bw = R >= 128 ? 128 : R; p.bh = 128 / p.bw;
+    p.bias = w.bias; p.residual = residual;
+    const uint64_t adims[4] = {(uint64_t)w.cin, (uint64_t)R + 2, (uint64_t)R + 2, (uint64_t)nb};
+    const uint32_t abox[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, 1};
+    const uint64_t odims[2] = {(uint64_t)w.cout, (uint64_t)nb * R * R};
+    const uint32_t obox[2] = {32, 32};
+    CUtensorMap *tahi, *talo, *tout;
+    MB_TRY(cached_tmap(h, &tahi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4, h->act_hi, adims, abox));
+    MB_TRY(cached_tmap(h, &talo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4, h->act_lo, adims, abox));
+    MB_TRY(cached_tmap(h, &tout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 2, out, odims, obox));
+    const int tiles = nb * (R / p.bh) * (R / p.bw) * (w.cout / ConvTcCfg::BN);
+    const int grid = tiles < h->num_sms ? tiles : h->num_sms;
     ProfScope prof(h, MB_PROF_DEC_CONV, st);
-    conv_igemm_kernel<<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(p);
+    conv_tcgen05_kernel<<<grid, 384, ConvTcCfg::SMEM_BYTES, st>>>(*tahi, *talo, w.tm_hi, w.tm_lo, *tout, p);
     CU_TRY(cudaGetLastError()); h->launches++;
     return 0;
 }

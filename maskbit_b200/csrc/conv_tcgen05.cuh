@@ -1,0 +1,246 @@
+// Decoder convolutions on tcgen05 (reference autoencoder.py:7-36 Conv2dSame, :84-96 ResidualBlock, :224-225 upsample conv).
+//
+// A 3x3 (or 1x1) stride-1 SAME convolution over NHWC activations is a GEMM  out[pixel, cout] = sum_{tap, cin} A * W  with
+//   M = pixels (tile: 128 consecutive pixels = bh full rows, or half a row at W = 256), N = 128 output channels,
+//   K = taps x Cin consumed in chunks of 64 channels of one tap.
+// The 1e-3-abs pixel bar against the fp32 reference rules out single-pass bf16 (8e-2 measured), so both operands are split
+// into bf16 hi + lo and every K-step issues three MMAs (hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM): ~2^-16 relative.
+//
+//   act_split_kernel      fp32 NHWC -> GroupNorm-apply + SiLU (optional) -> nearest x2 upsample (optional) -> bf16 hi / lo
+//                         written into a zero-bordered [N, H+2, W+2, C] tensor, so that every tap of every tile is a plain
+//                         TMA box (no im2col gather, no boundary predicates in the conv kernel)
+//   conv_tcgen05_kernel   persistent, warp-specialised like the GEMM: TMA producer (A_hi, A_lo boxes of the tap-shifted
+//                         padded input + W_hi, W_lo tiles) | one MMA thread (12 tcgen05.mma per stage) | 8 epilogue warps
+//                         (bias, fp32 residual, fp32 NHWC output through smem + TMA store)
+#pragma once
+#include "ptx.cuh"
+
+namespace mb {
+
+// ------------------------------------------------------------------------------------------------ activation transform
+// in    fp32 NHWC [N, Hin, Win, C]  (Hin = H >> up)
+// scale / shift  [N][C] GroupNorm-apply coefficients or nullptr (no norm, no SiLU)
+// hi/lo bf16 [N, H+2, W+2, C], border = 0
+__global__ void __launch_bounds__(256)
+act_split_kernel(const float* __restrict__ in, const float* __restrict__ scale, const float* __restrict__ shift,
+                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int N, int H, int W, int C, int up) {
+    const int c8 = C >> 3;                                      // 8-channel groups per pixel
+    const long long total = (long long)N * (H + 2) * (W + 2) * c8;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cg = (int)(idx % c8);
+    const long long pp = idx / c8;
+    const int xp = (int)(pp % (W + 2)), yp = (int)((pp / (W + 2)) % (H + 2)), n = (int)(pp / ((long long)(W + 2) * (H + 2)));
+    uint4 oh = make_uint4(0, 0, 0, 0), ol = make_uint4(0, 0, 0, 0);
+    if (xp >= 1 && xp <= W && yp >= 1 && yp <= H) {
+        const int Hin = H >> up, Win = W >> up;
+        const int ys = (yp - 1) >> up, xs = (xp - 1) >> up;
+        const float4* src = reinterpret_cast<const float4*>(in + (((size_t)n * Hin + ys) * Win + xs) * C + cg * 8);
+        float4 a = __ldg(src), b = __ldg(src + 1);
+        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        if (scale) {
+            const float4* sp = reinterpret_cast<const float4*>(scale + (size_t)n * C + cg * 8);
+            const float4* hp = reinterpret_cast<const float4*>(shift + (size_t)n * C + cg * 8);
+            const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1), h0 = __ldg(hp), h1 = __ldg(hp + 1);
+            const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            const float h[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float t = fmaf(v[i], s[i], h[i]);
+                v[i] = t / (1.0f + __expf(-t));                   // SiLU
+            }
+        }
+        uint32_t wh[4], wl[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
+            wh[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            wl[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        oh = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+        ol = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+    }
+    reinterpret_cast<uint4*>(hi)[idx] = oh;
+    reinterpret_cast<uint4*>(lo)[idx] = ol;
+}
+
+// ------------------------------------------------------------------------------------------------ conv kernel
+struct ConvTcParams {
+    int n_img, H, W, Cin, Cout, taps;   // taps = 9 (3x3) or 1 (1x1)
+    int bw, bh;                         // pixel tile = bh rows x bw columns, bw * bh = 128
+    const float* bias;                  // [Cout] or nullptr
+    const float* residual;              // fp32 NHWC [n_img*H*W, Cout] or nullptr
+};
+
+struct ConvTcCfg {
+    static constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+    static constexpr int TILE_BYTES = 128 * BK * 2;                    // every operand tile: 128 rows x 64 bf16
+    static constexpr int STAGE_BYTES = 4 * TILE_BYTES;                 // A_hi, A_lo, W_hi, W_lo
+    static constexpr int STG_BYTES = 8 * 4096;                         // output staging: 8 warps x (32 rows x 32 fp32)
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 + 256;
+};
+
+__device__ __forceinline__ void tma_load_4d_b(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    tma_load_4d(smem_dst, m, bar, c0, c1, c2, c3);
+}
+
+// tm_ahi / tm_alo : 4D maps of the padded bf16 inputs {C, W+2, H+2, N}, box {64, bw, bh, 1}
+// tm_whi / tm_wlo : 2D maps of the packed weights [Cout][taps*Cin], box {64, 128}
+// tm_out          : 2D map of the fp32 output [n_img*H*W, Cout], box {32, 32}
+__global__ void __launch_bounds__(384, 1)
+conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
+                    const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
+                    const __grid_constant__ CUtensorMap tm_out, ConvTcParams p) {
+    using C = ConvTcCfg;
+    constexpr int BN = C::BN, STAGES = C::STAGES;
+    extern __shared__ uint8_t cv_smem_raw[];
+    const uint32_t raw = smem_u32(cv_smem_raw);
+    uint8_t* base = cv_smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    uint8_t* smem_stg = base + STAGES * C::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + C::STG_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_x = p.W / p.bw, tiles_y = p.H / p.bh;
+    const int pix_tiles = p.n_img * tiles_y * tiles_x;
+    const int num_n = p.Cout / BN;
+    const int num_tiles = pix_tiles * num_n;
+    const int kchunks = p.Cin / C::BK;
+    const int num_k = p.taps * kchunks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_ahi); tma_prefetch_desc(&tm_alo); tma_prefetch_desc(&tm_whi); tma_prefetch_desc(&tm_wlo);
+        tma_prefetch_desc(&tm_out);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---------------- TMA producer
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int pt = tile / num_n, n_blk = tile - pt * num_n;
+                const int xb = pt % tiles_x, yb = (pt / tiles_x) % tiles_y, img = pt / (tiles_x * tiles_y);
+                const int x0 = xb * p.bw, y0 = yb * p.bh;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    const int tap = kb / kchunks, c0 = (kb - tap * kchunks) * C::BK;
+                    // 3x3: padded input pixel of output (y, x) under tap (dy, dx) is (y + dy, x + dx), dy, dx in 0..2;
+                    // 1x1: the centre (y + 1, x + 1)
+                    const int dy = p.taps == 9 ? tap / 3 : 1, dx = p.taps == 9 ? tap % 3 : 1;
+                    uint8_t* sb = base + stage * C::STAGE_BYTES;
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+                    tma_load_4d(sb, &tm_ahi, &full[stage], c0, x0 + dx, y0 + dy, img);
+                    tma_load_4d(sb + C::TILE_BYTES, &tm_alo, &full[stage], c0, x0 + dx, y0 + dy, img);
+                    tma_load_2d(sb + 2 * C::TILE_BYTES, &tm_whi, &full[stage], tap * p.Cin + c0, n_blk * BN);
+                    tma_load_2d(sb + 3 * C::TILE_BYTES, &tm_wlo, &full[stage], tap * p.Cin + c0, n_blk * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ---------------- MMA issuer: D += A_lo W_hi + A_hi W_lo + A_hi W_hi (small terms first)
+            constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, 128, BN);
+            int stage = 0; uint32_t phase = 0; uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sb = smem_u32(base + stage * C::STAGE_BYTES);
+                    const uint64_t ahi = make_sdesc_k128(sb), alo = make_sdesc_k128(sb + C::TILE_BYTES);
+                    const uint64_t whi = make_sdesc_k128(sb + 2 * C::TILE_BYTES), wlo = make_sdesc_k128(sb + 3 * C::TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < C::BK / 16; ++k) {
+                        umma_f16(d_tmem, alo + 2 * k, whi + 2 * k, idesc, (kb | k) != 0);
+                        umma_f16(d_tmem, ahi + 2 * k, wlo + 2 * k, idesc, 1);
+                        umma_f16(d_tmem, ahi + 2 * k, whi + 2 * k, idesc, 1);
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[as]);
+            }
+        }
+    } else if (warp >= 4) {  // ---------------- epilogue: + bias + residual -> fp32 NHWC via smem + TMA store
+        const int quarter = warp & 3, half = (warp - 4) >> 2;
+        uint8_t* stg = smem_stg + (warp - 4) * 4096;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int pt = tile / num_n, n_blk = tile - pt * num_n;
+            const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+            const long long row0 = (long long)pt * 128 + quarter * 32;     // tiles enumerate pixels in NHWC order
+            const long long row = row0 + lane;
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < BN / 2; c += 32) {
+                const int col0 = half * (BN / 2) + c;
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + col0, v);
+                tmem_ld_wait();
+                const int n0 = n_blk * BN + col0;
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if (p.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                        f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                    }
+                }
+                if (p.residual) {
+                    const float4* rp = reinterpret_cast<const float4*>(p.residual + (size_t)row * p.Cout + n0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 r4 = __ldg(rp + j);
+                        f[4 * j] += r4.x; f[4 * j + 1] += r4.y; f[4 * j + 2] += r4.z; f[4 * j + 3] += r4.w;
+                    }
+                }
+                if (lane == 0) tma_store_wait_read<0>();            // previous store finished reading the staging buffer
+                __syncwarp();
+                uint8_t* rowp = stg + lane * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                fence_async_proxy();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tm_out, stg, n0, (int)row0);
+                    tma_store_commit();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<2 * BN>(tmem_base);
+    }
+}
+
+}  // namespace mb
