@@ -622,16 +622,16 @@ static int launch_gemm2(mb_handle* h, const CUtensorMap& ta, const CUtensorMap& 
     if (tiles < pairs) pairs = tiles;
     const int grid = 2 * pairs, smem = Gemm2Cfg::SMEM_BYTES;
     switch (epi) {
-        case 0: gemm2_bf16_tcgen05_kernel<0><<<grid, 384, smem, st>>>(ta, tb, tc, p); break;
-        case 1: gemm2_bf16_tcgen05_kernel<1><<<grid, 384, smem, st>>>(ta, tb, tc, p); break;
-        case 2: gemm2_bf16_tcgen05_kernel<2><<<grid, 384, smem, st>>>(ta, tb, tc, p); break;
-        case 3: gemm2_bf16_tcgen05_kernel<3><<<grid, 384, smem, st>>>(ta, tb, tc, p); break;
-        case 4: gemm2_bf16_tcgen05_kernel<4><<<grid, 384, smem, st>>>(ta, tb, tc, p); break;
-        case 5: gemm2_bf16_tcgen05_kernel<5><<<grid, 384, smem, st>>>(ta, tb, tc, p); break;
-        case 6: gemm2_bf16_tcgen05_kernel<6><<<grid, 384, smem, st>>>(ta, tb, tc, p); break;
-        case 7: gemm2_bf16_tcgen05_kernel<7><<<grid, 384, smem, st>>>(ta, tb, tc, p); break;
-        case 8: gemm2_bf16_tcgen05_kernel<8><<<grid, 384, smem, st>>>(ta, tb, tc, p); break;
-        case 9: gemm2_bf16_tcgen05_kernel<9><<<grid, 384, smem, st>>>(ta, tb, tc, p); break;
+        case 0: gemm2_bf16_tcgen05_kernel<0><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, p); break;
+        case 1: gemm2_bf16_tcgen05_kernel<1><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, p); break;
+        case 2: gemm2_bf16_tcgen05_kernel<2><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, p); break;
+        case 3: gemm2_bf16_tcgen05_kernel<3><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, p); break;
+        case 4: gemm2_bf16_tcgen05_kernel<4><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, p); break;
+        case 5: gemm2_bf16_tcgen05_kernel<5><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, p); break;
+        case 6: gemm2_bf16_tcgen05_kernel<6><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, p); break;
+        case 7: gemm2_bf16_tcgen05_kernel<7><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, p); break;
+        case 8: gemm2_bf16_tcgen05_kernel<8><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, p); break;
+        case 9: gemm2_bf16_tcgen05_kernel<9><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, p); break;
         default: return fail(MB_ERR_INVALID, "bad epilogue %d", epi);
     }
     CU_TRY(cudaGetLastError());
@@ -643,13 +643,13 @@ static int launch_gemm2(mb_handle* h, const CUtensorMap& ta, const CUtensorMap& 
 static int launch_gemm(mb_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tb_half, const CUtensorMap* tc,
                        int BN, const GemmParams& p, int epi, int num_sms, cudaStream_t st) {
     if (g_use_2cta && tb_half && (tc || !gemm2_tma_store(epi)) && BN == 256 && p.K % 64 == 0 && p.N % 256 == 0 && num_sms >= 2) {
-        if ((epi == EPI_RES_LN_BF16_STATS || epi == EPI_LNIN_GELU_BF16_STATS) && p.N != 256 * (LN_PARTIALS / 2))
-            return fail(MB_ERR_INVALID, "row-statistics epilogue needs N=%d (got N=%d)", 256 * (LN_PARTIALS / 2), p.N);
+        if ((epi == EPI_RES_LN_BF16_STATS || epi == EPI_LNIN_GELU_BF16_STATS) && p.N != 64 * LN_PARTIALS)
+            return fail(MB_ERR_INVALID, "row-statistics epilogue needs N=%d (got N=%d)", 64 * LN_PARTIALS, p.N);
         return launch_gemm2(h, ta, *tb_half, tc ? *tc : ta, p, epi, num_sms, st);
     }
     if (p.K % 64 || p.N % BN) return fail(MB_ERR_INVALID, "gemm shape M=%d N=%d K=%d BN=%d", p.M, p.N, p.K, BN);
-    if ((epi == EPI_RES_LN_BF16_STATS || epi == EPI_LNIN_GELU_BF16_STATS) && (BN != 256 || p.N != 256 * (LN_PARTIALS / 2)))
-        return fail(MB_ERR_INVALID, "row-statistics epilogue needs N=%d, BN=256 (got N=%d BN=%d)", 256 * (LN_PARTIALS / 2), p.N, BN);
+    if ((epi == EPI_RES_LN_BF16_STATS || epi == EPI_LNIN_GELU_BF16_STATS) && (BN != 256 || p.N != 64 * LN_PARTIALS))
+        return fail(MB_ERR_INVALID, "row-statistics epilogue needs N=%d, BN=256 (got N=%d BN=%d)", 64 * LN_PARTIALS, p.N, BN);
     if (BN == 256) return launch_gemm_bn<256>(h, ta, tb, p, epi, num_sms, st);
     if (BN == 128) return launch_gemm_bn<128>(h, ta, tb, p, epi, num_sms, st);
     if (BN == 64) return launch_gemm_bn<64>(h, ta, tb, p, epi, num_sms, st);

@@ -4,14 +4,14 @@
 // grid = #SMs, one CTA per SM looping over (sequence, head) work items; 12 warps:
 //   warp 0      TMA producer: Q / K / V of the item (3 x 256 rows x 64 dims, 128B swizzle) + 16-row boxes holding the
 //               class-token rows (row 256 of Q, K, V) into a 2-stage shared-memory ring
-//   warp 1      MMA issuer (one thread), data driven: per 128-query tile t
+//   warps 1,2   MMA issuers (one thread each, one per 128-query tile t):
 //                   S_t = Q_t K^T            tcgen05.mma M128 N256 K16 x4, smem x smem
 //                   O_t = P_t V              A = P from TMEM, B = V MN-major from smem, 16 K-steps split over two
 //                                            accumulators (even / odd steps): dependent small MMAs are latency bound
-//   warps 2,3   the 257th row and column, alternating items, on warp-level mma.sync tiles:
+//   warp 3      the 257th row and column on warp-level mma.sync tiles:
 //                   s256[q] = Q[q] . K[256] for the 256 tile queries -> smem (the class-token KEY column)
 //                   the class-token QUERY row q = 256 against all 257 keys, softmax, P V -> global
-//               warp 3 also allocates TMEM (512 columns)
+//               (also allocates TMEM, 512 columns)
 //   warps 4-11  softmax: warpgroup t owns query tile t, thread = one query row.  Pass 1 row max over S_t in TMEM,
 //               pass 2 exp2 -> bf16 P written back over the S columns already consumed (FFMA2 + MUFU + F2FP + FADD2),
 //               epilogue (O_a + O_b + p256 V[256]) / l -> bf16 -> global.  The two warpgroups take turns in pass 2
@@ -139,7 +139,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
     float* s256buf = reinterpret_cast<float*>(base + 2 * ATC_STAGE_BYTES);           // [2 stages][256 queries]
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + 2 * ATC_STAGE_BYTES + ATC_S256_BYTES);
     uint64_t* full = bars;           // [2] TMA landed
-    uint64_t* empty = bars + 2;      // [2] stage consumed (MMA commit + 8 softmax warps + class warp)
+    uint64_t* empty = bars + 2;      // [2] stage consumed (2 MMA issuers' commits + 8 softmax warps + class warp)
     uint64_t* s_full = bars + 4;     // [2] S_t complete in TMEM
     uint64_t* p_full = bars + 6;     // [2] P_t written to TMEM (4 warps)
     uint64_t* o_full = bars + 8;     // [2] O_t complete
@@ -151,7 +151,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_big); tma_prefetch_desc(&tm_row); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&full[s], 1); mbar_init(&empty[s], 10);
+            mbar_init(&full[s], 1); mbar_init(&empty[s], 11);
             mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 4); mbar_init(&o_full[s], 1); mbar_init(&t_free[s], 4);
             mbar_init(&cls_ready[s], 1);
         }
@@ -184,59 +184,47 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
                 tma_load_2d(sb + 3 * ATC_TILE_BYTES + 2 * ATC_ROW_BYTES, &tm_row, &full[st], 2 * p.D + col, row0 + 256);  // V[256..]
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {  // ---------------------------------------------------------------- MMA issuer
+    } else if (warp == 1 || warp == 2) {
+        if (lane == 0) {  // ---------------------------------------------------------------- MMA issuers: warp 1 -> tile 0, warp 2 -> tile 1
+            // One issuing thread per query tile: issuing a chain of dependent small MMAs blocks the thread for ~100 cycles per
+            // instruction, so a single issuer would hold back the other tile's S / PV groups behind it.
             constexpr uint32_t idesc_s = make_idesc(1, 128, 256);
             constexpr uint32_t idesc_o = make_idesc(1, 128, 64) | (1u << 16);   // B (= V) is MN-major
-            // Data-driven issue order: the two query tiles are independent pipelines (S_t -> softmax -> P_t V -> epilogue);
-            // whichever MMA group has its inputs ready is issued next (non-blocking barrier probes).
-            int it_s[2] = {0, 0}, it_p[2] = {0, 0};
-            long long t_poll = clock64();
-            while (it_p[0] < n_local || it_p[1] < n_local) {
-                bool progressed = false;
+            const int t = warp - 1;
+            const uint32_t tr = tmem_base + t * 256;
+            for (int it = 0; it < n_local; ++it) {
+                const int st = it & 1;
+                const uint32_t sq = smem0 + st * ATC_STAGE_BYTES, sk = sq + ATC_TILE_BYTES, sv = sk + ATC_TILE_BYTES;
+                mbar_wait(&full[st], (it >> 1) & 1);
+                mbar_wait(&t_free[t], (it & 1) ^ 1);
+                tc_fence_after();
+                {                                                               // S_t = Q_t K^T
+                    const uint64_t a = make_sdesc_k128(sq + t * 128 * 128), b = make_sdesc_k128(sk);
 #pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    const uint32_t tr = tmem_base + t * 256;
-                    if (it_s[t] < n_local && it_s[t] == it_p[t]) {                 // S_t = Q_t K^T of item it_s[t]
-                        const int it = it_s[t], st = it & 1;
-                        if (mbar_test_wait(&full[st], (it >> 1) & 1) && mbar_test_wait(&t_free[t], (it & 1) ^ 1)) {
-                            tc_fence_after();
-                            const uint32_t sq = smem0 + st * ATC_STAGE_BYTES, sk = sq + ATC_TILE_BYTES;
-                            const uint64_t a = make_sdesc_k128(sq + t * 128 * 128), b = make_sdesc_k128(sk);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) umma_f16(tr, a + 2 * k, b + 2 * k, idesc_s, k != 0);
-                            umma_commit(&s_full[t]);
-                            ATC_EV(1, t, it);
-                            it_s[t]++; progressed = true;
-                        }
-                    }
-                    if (it_p[t] < it_s[t]) {                                       // O_t = P_t V
-                        const int it = it_p[t], st = it & 1;
-                        if (mbar_test_wait(&p_full[t], it & 1)) {
-                            tc_fence_after();
-                            const uint64_t b = make_sdesc_mn128(smem0 + st * ATC_STAGE_BYTES + 2 * ATC_TILE_BYTES);
-#pragma unroll
-                            for (int j = 0; j < 16; ++j)       // even key blocks -> O_a, odd -> O_b: two independent chains
-                                umma_f16_ts(tr + 128 + 64 * (j & 1), tr + 8 * j, b + (uint64_t)(j * 128), idesc_o, j >= 2);
-                            umma_commit(&o_full[t]);
-                            ATC_EV(1, 2 + t, it);
-                            it_p[t]++; progressed = true;
-                            if (it_p[t ^ 1] > it) umma_commit(&empty[st]);         // both tiles of the item have read the stage
-                        }
-                    }
+                    for (int k = 0; k < 4; ++k) umma_f16(tr, a + 2 * k, b + 2 * k, idesc_s, k != 0);
+                    umma_commit(&s_full[t]);
+                    ATC_EV(1, t, it);
                 }
-                if (progressed) t_poll = clock64();
-                else if (clock64() - t_poll > MB_WAIT_TIMEOUT_CYCLES) { printf("attention MMA issuer timeout: block %d\n", (int)blockIdx.x); __trap(); }
+                mbar_wait(&p_full[t], it & 1);
+                tc_fence_after();
+                {                                                               // O_t = P_t V
+                    const uint64_t b = make_sdesc_mn128(sv);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)       // even key blocks -> O_a, odd -> O_b: two independent chains
+                        umma_f16_ts(tr + 128 + 64 * (j & 1), tr + 8 * j, b + (uint64_t)(j * 128), idesc_o, j >= 2);
+                    umma_commit(&o_full[t]);
+                    umma_commit(&empty[st]);                                    // this tile's MMAs have read the stage
+                    ATC_EV(1, 2 + t, it);
+                }
             }
         }
-    } else if (warp == 2 || warp == 3) {  // -------------------------------------------- the 257th row and column
+    } else if (warp == 3) {  // -------------------------------------------------------------- the 257th row and column
         // One query row / one key column is too small for a tcgen05 tile and too slow as scalar FMAs, so both run on the
         // warp-level tensor path: mma.sync m16n8k16 with a single live row (or column) in one operand, the other operand
-        // via ldmatrix from the swizzled TMA tiles.  Warps 2 and 3 alternate work items.
+        // via ldmatrix from the swizzled TMA tiles.
         uint32_t it = 0;
         const int g = lane >> 2, t4 = lane & 3;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-            if ((it & 1) != (uint32_t)(warp - 2)) continue;
             const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
             const int seq = item / p.H, head = item - seq * p.H;
             const uint32_t sq = smem0 + st * ATC_STAGE_BYTES, sk = sq + ATC_TILE_BYTES, sv = sk + ATC_TILE_BYTES;

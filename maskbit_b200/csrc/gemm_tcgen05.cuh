@@ -43,7 +43,7 @@ enum EpiMode : int {
     EPI_LNIN_F32_SEQ = 9,         // out fp32 = rstd*(acc - mean*u) + c, class row dropped            (prediction layer)
 };
 constexpr int GEMM_NUM_EPI = 10;
-constexpr int LN_PARTIALS = 8;    // partial (sum, sumsq) slots per row: one per (256-wide n-block, 128-column half) of a 1024-wide row
+constexpr int LN_PARTIALS = 16;   // partial (sum, sumsq) slots per row: one per 64-column block of a 1024-wide row
 
 struct GemmParams {
     int M, N, K;
@@ -123,6 +123,41 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
     x0 = h0; x1 = h1;
 }
 
+// The same two GELUs without the MUFU pipe: Phi(x) - 0.5 = x * Q(x^2), Q a degree-9 least-squares polynomial on x^2 <= 4.5^2
+// (|x| clamped beyond: Phi(4.5) = 1 - 3.4e-6); |gelu error| <= 5e-5 at |x| ~ 4.5 and ~1e-5 elsewhere, far below the bf16
+// rounding of the stored value.  The GELU epilogue alternates the two forms pair by pair: with erf on the MUFU form alone
+// the special-function pipe (16 ops / clk / SM, two per element) is as busy as the tensor pipe over a 128 x 256 x 1024 tile.
+__device__ __forceinline__ void gelu_poly2(float& x0, float& x1) {
+    constexpr float L = 4.5f;
+    const float c0 = fminf(fmaxf(x0, -L), L), c1 = fminf(fmaxf(x1, -L), L);
+    float q0, q1;
+    asm("{\n\t.reg .b64 rt, rq, rk, rc;\n\t"
+        "mov.b64 rc, {%2, %3};\n\tmul.rn.f32x2 rt, rc, rc;\n\t"                 // t = clamp(x)^2
+        "mov.b64 rq, {%4, %4};\n\tmov.b64 rk, {%5, %5};\n\tfma.rn.f32x2 rq, rq, rt, rk;\n\t"
+        "mov.b64 rk, {%6, %6};\n\tfma.rn.f32x2 rq, rq, rt, rk;\n\t"
+        "mov.b64 rk, {%7, %7};\n\tfma.rn.f32x2 rq, rq, rt, rk;\n\t"
+        "mov.b64 rk, {%8, %8};\n\tfma.rn.f32x2 rq, rq, rt, rk;\n\t"
+        "mov.b64 rk, {%9, %9};\n\tfma.rn.f32x2 rq, rq, rt, rk;\n\t"
+        "mov.b64 rk, {%10, %10};\n\tfma.rn.f32x2 rq, rq, rt, rk;\n\t"
+        "mov.b64 rk, {%11, %11};\n\tfma.rn.f32x2 rq, rq, rt, rk;\n\t"
+        "mov.b64 rk, {%12, %12};\n\tfma.rn.f32x2 rq, rq, rt, rk;\n\t"
+        "mov.b64 rk, {%13, %13};\n\tfma.rn.f32x2 rq, rq, rt, rk;\n\t"
+        "mul.rn.f32x2 rq, rq, rc;\n\t"                                             // Phi - 0.5 = clamp(x) * Q
+        "mov.b64 {%0, %1}, rq;\n\t}"
+        : "=f"(q0), "=f"(q1)
+        : "f"(c0), "f"(c1), "f"(-1.334576828e-12f), "f"(1.631205285e-10f), "f"(-8.910449133e-09f), "f"(2.891752189e-07f),
+          "f"(-6.269251990e-06f), "f"(9.702424500e-05f), "f"(-1.118151080e-03f), "f"(9.819429864e-03f), "f"(-6.631637927e-02f),
+          "f"(3.988728748e-01f));
+    x0 = fmaf(x0, q0, 0.5f * x0);
+    x1 = fmaf(x1, q1, 0.5f * x1);
+}
+
+__device__ __forceinline__ void st_global_v8(void* ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                                             uint32_t g, uint32_t h) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
+}
+
 // mean and rstd of a row from its LN_PARTIALS partial sums
 __device__ __forceinline__ void ln_row_stats(const float2* __restrict__ st, float inv_d, float eps, float& mean, float& rstd) {
     const float4* q = reinterpret_cast<const float4*>(st);
@@ -171,8 +206,8 @@ struct EpiStage {
 };
 
 // taddr: TMEM address of this warp's lane quarter at column 0 of the accumulator tile; the warp handles columns
-// [half * BN/2, (half+1) * BN/2) of the BN-wide tile n_blk.  kTma: bf16 output through smem + cp.async.bulk.tensor store.
-template <int BN, int EPI, bool kTma = false>
+// [part * BN/NSPLIT, (part+1) * BN/NSPLIT) of the BN-wide tile n_blk.  kTma: bf16 output through smem + cp.async.bulk.tensor store.
+template <int BN, int EPI, bool kTma = false, int NSPLIT = 2>
 __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, uint32_t taddr, int n_blk, int half,
                                         EpiStage stg = EpiStage{nullptr, nullptr, 0}) {
     constexpr bool kLnIn = EPI == EPI_LNIN_BF16 || EPI == EPI_LNIN_GELU_BF16 || EPI == EPI_LNIN_GELU_BF16_STATS || EPI == EPI_LNIN_F32_SEQ;
@@ -180,7 +215,7 @@ __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, u
     constexpr bool kStats = EPI == EPI_RES_LN_BF16_STATS || EPI == EPI_LNIN_GELU_BF16_STATS;
     constexpr bool kOutBf16 = EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_LNIN_BF16 || EPI == EPI_LNIN_GELU_BF16 ||
                               EPI == EPI_RES_LN_BF16_STATS || EPI == EPI_LNIN_GELU_BF16_STATS;
-    constexpr int COLS_PER_WARP = BN / 2;
+    constexpr int COLS_PER_WARP = BN / NSPLIT;
     const int row = er.row;
     const bool row_ok = er.row_ok, store_ok = er.store_ok;
     const long long out_row = er.out_row;
@@ -212,7 +247,7 @@ __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, u
         }
         if (kGelu && !GEMM_TIMING_NO_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) gelu_erf2(f[j], f[j + 1]);
+            for (int j = 0; j < 32; j += 4) { gelu_erf2(f[j], f[j + 1]); gelu_poly2(f[j + 2], f[j + 3]); }
         }
         if (EPI == EPI_BIAS_RES_F32 || EPI == EPI_RES_LN_BF16_STATS) {
             if (row_ok) {
@@ -272,9 +307,10 @@ __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, u
                     }
                 }
             } else if (store_ok && !GEMM_TIMING_NO_STORE) {
-                uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (size_t)out_row * p.ldo + n0);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) op[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+                // 256-bit stores: every lane writes whole 32-byte sectors of its own row
+                __nv_bfloat16* op = static_cast<__nv_bfloat16*>(p.out) + (size_t)out_row * p.ldo + n0;
+                st_global_v8(op, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+                st_global_v8(op + 16, w[8], w[9], w[10], w[11], w[12], w[13], w[14], w[15]);
             }
         } else if (store_ok) {
             float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + (size_t)out_row * p.ldo + n0);
@@ -282,7 +318,12 @@ __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, u
             for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
         }
     }
-    if (kStats && row_ok) p.stats_out[(size_t)row * LN_PARTIALS + n_blk * 2 + half] = make_float2(st_sum, st_sq);
+    if (kStats && row_ok) {   // slot = 64-column block index of the warp's first column; a wider warp slab zeroes the slots it spans
+        float2* so = p.stats_out + (size_t)row * LN_PARTIALS + (n_blk * BN + half * COLS_PER_WARP) / 64;
+        so[0] = make_float2(st_sum, st_sq);
+#pragma unroll
+        for (int i = 1; i < COLS_PER_WARP / 64; ++i) so[i] = make_float2(0.f, 0.f);
+    }
 }
 
 template <int BN, int EPI>
@@ -390,24 +431,33 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 // a third less L2 -> SM traffic and shared-memory fill per MMA (the 1-CTA kernel is bound there, not in the tensor pipe),
 // which also makes room for 6 pipeline stages instead of 4.
 //   leader CTA (cluster rank 0): arms full[s] for the bytes of BOTH CTAs and issues every MMA;
-//   both CTAs: TMA producer for their own halves (completion signalled on the leader's full[s]), epilogue of their own rows;
+//   both CTAs: TMA producer for their own halves (completion signalled on the leader's full[s]), epilogue of their own rows
+//   by 8 warps;
 //   tcgen05.commit multicasts the "stage consumed" / "accumulator ready" arrivals to both CTAs; the epilogue warps of both
 //   CTAs release the accumulator stage on the leader's tmem_empty barrier.
 struct Gemm2Cfg {
     static constexpr int BM = 256, BN = 256, BK = 64, STAGES = 6;
+    // 4 TMEM lane quarters x 2 column halves.  16 warps (4 x 4, 5 stages to make room for their staging) measured SLOWER on
+    // every GEMM (QKV 1435 -> 1249, up 1272 -> 1146 TFLOP/s): the extra warps and the lost stage cost more than the added
+    // epilogue parallelism buys.
+    static constexpr int EPI_WARPS = 8;
+    static constexpr int THREADS = 128 + EPI_WARPS * 32;
     static constexpr int A_BYTES = 128 * BK * 2;      // per CTA
     static constexpr int B_BYTES = 128 * BK * 2;      // per CTA (half of the 256 weight rows)
-    static constexpr int STG_BYTES = 8 * 4096;        // output staging: 8 epilogue warps x (32 rows x 128 B)
+    static constexpr int STG_BYTES = EPI_WARPS * 4096; // output staging: per epilogue warp 32 rows x 128 B
     static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + STG_BYTES + 1024 + 256;
 };
 // bf16-output epilogues of the CTA-pair kernel go through shared memory and TMA stores
+#ifndef GEMM2_DIRECT256
+#define GEMM2_DIRECT256 0   // 1: CTA-pair kernel stores straight from registers with 256-bit stores instead of smem + TMA
+#endif
 __host__ __device__ constexpr bool gemm2_tma_store(int epi) {
-    return epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_LNIN_BF16 || epi == EPI_LNIN_GELU_BF16 ||
-           epi == EPI_RES_LN_BF16_STATS || epi == EPI_LNIN_GELU_BF16_STATS;
+    return !GEMM2_DIRECT256 && (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_LNIN_BF16 || epi == EPI_LNIN_GELU_BF16 ||
+           epi == EPI_RES_LN_BF16_STATS || epi == EPI_LNIN_GELU_BF16_STATS);
 }
 
 template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg::THREADS, 1)
 gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                           const __grid_constant__ CUtensorMap tm_c, GemmParams p) {
     using C = Gemm2Cfg;
@@ -440,7 +490,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 16); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 2 * C::EPI_WARPS); }
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc_2sm<512>(tmem_slot);
@@ -487,7 +537,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
                 umma_commit_2sm(&tmem_full[as], 3);
             }
         }
-    } else if (warp >= 4) {  // ---------------- epilogue: each CTA its own 128 rows
+    } else if (warp >= 4) {  // ---------------- epilogue: each CTA its own 128 rows; warp = (lane quarter, 64-column quarter)
         const int quarter = warp & 3, half = (warp - 4) >> 2;
         uint32_t it = 0;
         for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
@@ -497,8 +547,8 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
             const EpiRow er = epi_prepare<EPI>(p, row0 + lane);
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
-            epi_run<BN, EPI, kTma>(p, er, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN, n_blk, half,
-                                   EpiStage{smem_stg + (warp - 4) * 4096, &tm_c, row0});
+            epi_run<BN, EPI, kTma, C::EPI_WARPS / 4>(p, er, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN, n_blk, half,
+                                                     EpiStage{smem_stg + (warp - 4) * 4096, &tm_c, row0});
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0));

@@ -88,6 +88,25 @@ def test_forward_matches_reference_golden(bits, golden_dir):
     assert (logits[:n] - logits[n:]).abs().max().item() > 1e-3
 
 
+@pytest.mark.parametrize("bits", [10, 16, 18])
+def test_forward_other_shipped_widths_vs_oracle(bits):
+    """The other shipped generator shapes (configs/generator/maskbit_generator_{10,16,18}bit.yaml: V = 32 / 256 / 512,
+    prediction width 64 / 512 / 1024) against the CPU oracle (itself pinned to the reference at 12 and 14 bit)."""
+    _, _, _, gen = models(bits)
+    v = 2 ** (bits // 2)
+    gcpu = torch.Generator().manual_seed(bits)
+    tok = torch.randint(0, v, (2, 256, 2), generator=gcpu)
+    tok[torch.rand((2, 256, 2), generator=gcpu) < 0.5] = v
+    labels = torch.tensor([17, 923])
+    drop = torch.tensor([False, True])
+    logits = gen(tok.cuda(), labels.cuda(), drop.cuda())
+    ref = O.lfq_bert_forward(gen.state_dict(), tok, labels, drop)
+    assert logits.shape == (2, 256, 2, v)
+    d = (logits.cpu() - ref).abs()
+    print(f"forward {bits}bit: max abs {d.max().item():.4e} mean abs {d.mean().item():.4e}")
+    assert d.max().item() <= LOGIT_MAX_ABS and d.mean().item() <= LOGIT_MEAN_ABS
+
+
 def test_forward_drop_none_and_batch_invariance(golden_dir):
     """drop_label_mask=None drops every label (the reference quirk `cls_token[None] = 1000`, bert.py:482-484), and a
     sequence's logits do not depend on what else is in the batch (bit-exact: tiles never mix sequences' rows)."""
