@@ -107,6 +107,12 @@ int mb_select_step(mb_handle* h, const mb_select_args* a, mb_stream stream);
  * -> images device fp32 [B, 3, H, W] (unclamped, NCHW like the reference). */
 int mb_decode_tokens(mb_handle* h, const int64_t* tokens, int B, float* images, mb_stream stream);
 
+/* ConvVQModel.encode (conv_vqgan.py:71-84; ConvEncoder autoencoder.py:230-286 + LookupFreeQuantizer.forward
+ * lookup_free.py:46-94): images device fp32 [B,3,H,W] (values as the data pipeline delivers them, [0,1]) ->
+ *   z        device fp32 [B, token_bits, P, P] encoder latents before the sign (or NULL)
+ *   indices  device int64 [B, P*P] tokens = sum_k [z_k > 0] << k (or NULL)                      (P*P = seq_len) */
+int mb_encode(mb_handle* h, const float* images, int B, float* z, int64_t* indices, mb_stream stream);
+
 /* combine_factorized_tokens (factorization.py:7-24): device int64 [B,n,splits] -> device int64 [B,n]. */
 int mb_combine_tokens(mb_handle* h, const int64_t* tokens, int B, int64_t* combined, mb_stream stream);
 

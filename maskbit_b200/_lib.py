@@ -52,6 +52,7 @@ SYMBOLS = {
     "mb_generator_forward": (_I, [_P, _P, _I, _P, _I, _P, _I, _P, _P]),
     "mb_select_step": (_I, [_P, ctypes.POINTER(MBSelectArgs), _P]),
     "mb_decode_tokens": (_I, [_P, _P, _I, _P, _P]),
+    "mb_encode": (_I, [_P, _P, _I, _P, _P, _P]),
     "mb_combine_tokens": (_I, [_P, _P, _I, _P, _P]),
     "mb_postprocess_u8": (_I, [_P, _P, _I, _P, _P]),
     "mb_sample": (_I, [_P, ctypes.POINTER(MBSampleArgs), _P]),

@@ -1,5 +1,5 @@
-"""ConvVQModel -- drop-in mirror of modeling/conv_vqgan.py:39-132 for the decode path
-(decode_tokens / decode); the convolutions run in libmaskbit_b200's kernels."""
+"""ConvVQModel -- drop-in mirror of modeling/conv_vqgan.py:39-132 (decode_tokens / decode / encode / forward); the
+convolutions run in libmaskbit_b200's kernels."""
 import ctypes
 
 import torch
@@ -89,8 +89,43 @@ class ConvVQModel(EngineModel):
                                                     ctypes.c_void_p(out.data_ptr()), _lib.current_stream()))
         return out
 
-    def encode(self, x):
-        raise NotImplementedError("tokenizer encode path (ConvEncoder + LFQ forward) is SURVEY.md 8(f) 'next', not built yet")
+    @torch.no_grad()
+    def tokenize(self, x, return_latents=False):
+        """Images fp32 [B,3,H,W] -> LFQ tokens int64 [B,16,16] (``min_encoding_indices`` of lookup_free.py:60) and, when
+        asked, the encoder latents z fp32 [B,bits,16,16] before the sign."""
+        h = self._engine()
+        dev = self._device
+        x = x.to(device=dev, dtype=torch.float32).contiguous()
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.image_size or x.shape[3] != self.image_size:
+            raise ValueError(f"expected images [B,3,{self.image_size},{self.image_size}], got {tuple(x.shape)}")
+        b = x.shape[0]
+        with torch.cuda.device(dev):
+            idx = torch.empty((b, 16, 16), dtype=torch.int64, device=dev)
+            z = torch.empty((b, self.token_size, 16, 16), dtype=torch.float32, device=dev) if return_latents else None
+            if b > 0:
+                _lib.check(_lib.lib().mb_encode(h, ctypes.c_void_p(x.data_ptr()), b, ctypes.c_void_p(z.data_ptr()) if z is not None else None,
+                                                ctypes.c_void_p(idx.data_ptr()), _lib.current_stream()))
+        return (idx, z) if return_latents else idx
 
+    @torch.no_grad()
+    def encode(self, x):
+        """conv_vqgan.py:71-84 in eval mode: (z_quantized [B,bits,16,16] with entries +-1, result_dict).  The reference returns
+        z + (sign(z) - z), i.e. +-1 up to fp32 rounding (lookup_free.py:80); here the entries are exactly +-1.  Losses are
+        training quantities: commitment_loss / quantizer_loss are evaluated from the latents, the entropy terms are 0 in
+        eval mode exactly as in the reference (lookup_free.py:64-74)."""
+        idx, z = self.tokenize(x, return_latents=True)
+        b2i = (2 ** torch.arange(self.token_size, device=idx.device)).view(1, -1, 1, 1)
+        zq = ((idx.unsqueeze(1) & b2i) != 0).float() * 2.0 - 1.0
+        zero = torch.zeros((), device=idx.device)
+        commitment = float(self.config.commitment_cost) * torch.mean((zq - z) ** 2)
+        result = dict(quantizer_loss=commitment, commitment_loss=commitment, entropy_loss=zero, per_sample_entropy=zero,
+                      avg_entropy=zero, min_encoding_indices=idx)
+        return zq, result
+
+    @torch.no_grad()
     def forward(self, x):
-        raise NotImplementedError("tokenizer encode path (ConvEncoder + LFQ forward) is SURVEY.md 8(f) 'next', not built yet")
+        """conv_vqgan.py:114-132: (reconstruction fp32 [B,3,H,W], result_dict)."""
+        zq, result = self.encode(x)
+        return self.decode_tokens(result["min_encoding_indices"].reshape(zq.shape[0], -1)), result
+
+    __call__ = forward

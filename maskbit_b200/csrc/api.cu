@@ -18,6 +18,7 @@
 #include "conv_tcgen05.cuh"
 #include "decoder.cuh"
 #include "embed_ln.cuh"
+#include "encoder.cuh"
 #include "gemm_tcgen05.cuh"
 #include "select.cuh"
 
@@ -159,6 +160,13 @@ __global__ void pack_conv_in_kernel(const float* __restrict__ w, float* __restri
     int tap = (int)(i % 9), k = (int)((i / 9) % bits), c = (int)(i / (9 * (size_t)bits));
     out[((size_t)tap * bits + k) * C + c] = w[i];
 }
+// encoder conv_in weight [C0][3][3][3] -> [27][C0]
+__global__ void pack_enc_conv_in_kernel(const float* __restrict__ w, float* __restrict__ out, int C0) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 27 * C0) return;
+    const int c = i / 27, t = i % 27;
+    out[t * C0 + c] = w[i];
+}
 // conv_out weight [3][C][3][3] -> [tap][C][4]
 __global__ void pack_conv_out_kernel(const float* __restrict__ w, float* __restrict__ out, int C) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -227,6 +235,13 @@ struct mb_handle {
     std::vector<ResBlockW> mid;
     std::vector<StageW> ups;
     GNW norm_out;
+    // encoder (tokenizer encode path, autoencoder.py:230-286)
+    float *enc_cin_w = nullptr, *enc_cout_w = nullptr, *enc_cout_b = nullptr;
+    int enc_c0 = 0, enc_cl = 0;
+    struct EncStage { std::vector<ResBlockW> blocks; bool has_down = false; ConvW down; };
+    std::vector<EncStage> enc_down;
+    std::vector<ResBlockW> enc_mid;
+    GNW enc_norm_out;
     int dec_cap = 0;
     float *dx = nullptr, *dt1 = nullptr, *dt2 = nullptr, *gn_scale = nullptr, *gn_shift = nullptr;
     double2* gn_partial = nullptr;
@@ -349,7 +364,6 @@ extern "C" int mb_set_tensor(mb_handle* h, int model, const char* name, const fl
     DevTensor t;
     t.numel = 1;
     for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); t.numel *= (size_t)shape[i]; }
-    if (model == MB_TOKENIZER && strncmp(name, "encoder.", 8) == 0) return 0;  // encode path not part of this library yet
     auto it = h->staged[model].find(name);
     if (it != h->staged[model].end()) { cudaFree(it->second.ptr); h->staged[model].erase(it); }
     CU_TRY(cudaMalloc(&t.ptr, t.numel * sizeof(float) + 16));
@@ -536,6 +550,38 @@ static int finalize_tokenizer(mb_handle* h) {
     CU_TRY(cudaDeviceSynchronize());
     cudaFree(t.ptr); h->staged[MB_TOKENIZER].erase("decoder.conv_out.weight");
     MB_TRY(keep_f32(h, MB_TOKENIZER, "decoder.conv_out.bias", {3}, &h->cout_b));
+    // ---- encoder
+    {
+        const int c0 = hc;
+        h->enc_c0 = c0;
+        MB_TRY(take(h, MB_TOKENIZER, "encoder.conv_in.weight", {c0, 3, 3, 3}, &t));
+        MB_TRY(dev_alloc(h, &h->enc_cin_w, (size_t)27 * c0));
+        pack_enc_conv_in_kernel<<<(27 * c0 + 255) / 256, 256>>>(t.ptr, h->enc_cin_w, c0);
+        CU_TRY(cudaDeviceSynchronize());
+        cudaFree(t.ptr); h->staged[MB_TOKENIZER].erase("encoder.conv_in.weight");
+        h->enc_down.resize(nr);
+        int cin_l = c0, cout_l = c0;
+        for (int lvl = 0; lvl < nr; ++lvl) {
+            cin_l = hc * (lvl == 0 ? 1 : c.dec_channel_mult[lvl - 1]);
+            cout_l = hc * c.dec_channel_mult[lvl];
+            auto& stg = h->enc_down[lvl];
+            stg.blocks.resize(c.dec_num_res_blocks);
+            for (int r = 0; r < c.dec_num_res_blocks; ++r)
+                MB_TRY(make_block(h, "encoder.down." + std::to_string(lvl) + ".res_blocks." + std::to_string(r) + ".", r == 0 ? cin_l : cout_l, cout_l, &stg.blocks[r]));
+            stg.has_down = lvl < nr - 1;
+            if (stg.has_down) MB_TRY(make_conv(h, "encoder.down." + std::to_string(lvl) + ".down_conv", cout_l, cout_l, 3, true, &stg.down));
+        }
+        h->enc_cl = cout_l;
+        h->enc_mid.resize(c.dec_num_res_blocks);
+        for (int r = 0; r < c.dec_num_res_blocks; ++r)
+            MB_TRY(make_block(h, "encoder.mid.res_blocks." + std::to_string(r) + ".", cout_l, cout_l, &h->enc_mid[r]));
+        MB_TRY(make_gn(h, "encoder.norm_out", cout_l, &h->enc_norm_out));
+        DevTensor tw;
+        MB_TRY(take(h, MB_TOKENIZER, "encoder.conv_out.weight", {h->bits, cout_l, 1, 1}, &tw));
+        h->allocs.push_back(tw.ptr); h->staged[MB_TOKENIZER].erase("encoder.conv_out.weight");
+        h->enc_cout_w = tw.ptr;                                              // [bits][C] as stored
+        MB_TRY(keep_f32(h, MB_TOKENIZER, "encoder.conv_out.bias", {h->bits}, &h->enc_cout_b));
+    }
     for (const char* nm : {"quantize.bits_to_indices", "quantize.codebook"}) {   // implicit codebook: bit k <-> 2^k
         auto it = h->staged[MB_TOKENIZER].find(nm);
         if (it == h->staged[MB_TOKENIZER].end()) return fail(MB_ERR_MISSING, "strict loading: missing key \"%s\"", nm);
@@ -833,6 +879,10 @@ static int ensure_dec_ws(mb_handle* h, int nb) {
         }
         const size_t e0 = (size_t)(P + 2) * (P + 2) * h->dec_c0; if (e0 > max_pad) max_pad = e0;
     }
+    {   // the encoder's first levels (stride-2 inputs at the full image size, 4 parity planes of ((R+2)/2)^2)
+        const int Rimg = P << (h->cfg.dec_num_resolutions - 1);
+        const size_t e = (size_t)(Rimg + 2) * (Rimg + 2) * h->enc_c0; if (e > max_pad) max_pad = e;
+    }
     MB_TRY(dev_alloc(h, &h->act_hi, max_pad * nb, false));
     MB_TRY(dev_alloc(h, &h->act_lo, max_pad * nb, false));
     h->dec_cap = nb;
@@ -863,27 +913,30 @@ static int cached_tmap(mb_handle* h, CUtensorMap** out, CUtensorMapDataType dt, 
     return 0;
 }
 // out = conv(act(in)) (+bias) (+residual): act = GroupNorm-apply + SiLU when gn, nearest x2 upsample when up (autoencoder.py:85-96,224-225)
+// R = OUTPUT resolution; stride 2 (encoder down convs, Conv2dSame pad 0/1, autoencoder.py:7-36,160) reads its input at 2R.
 static int run_conv(mb_handle* h, const float* in, float* out, const ConvW& w, int nb, int R, bool gn, int up, const float* residual,
-                    cudaStream_t st) {
-    if (R < 16 || (R & (R - 1))) return fail(MB_ERR_INVALID, "decoder resolution %d unsupported (power of two >= 16)", R);
+                    cudaStream_t st, int stride = 1) {
+    if (R < 16 || (R & (R - 1))) return fail(MB_ERR_INVALID, "conv resolution %d unsupported (power of two >= 16)", R);
+    const int Rin = R * stride;                                     // size of the (upsampled) conv input
     {
         ProfScope prof(h, MB_PROF_DEC_IO, st);
-        const long long total = (long long)nb * (R + 2) * (R + 2) * (w.cin / 8);
+        const long long total = (long long)nb * (Rin + 2) * (Rin + 2) * (w.cin / 8);
         act_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, gn ? h->gn_scale : nullptr, gn ? h->gn_shift : nullptr,
-                                                                          h->act_hi, h->act_lo, nb, R, R, w.cin, up);
+                                                                          h->act_hi, h->act_lo, nb, Rin, Rin, w.cin, up, stride == 2 ? 4 : 1);
         CU_TRY(cudaGetLastError()); h->launches++;
     }
     ConvTcParams p;
-    p.n_img = nb; p.H = R; p.W = R; p.Cin = w.cin; p.Cout = w.cout; p.taps = w.taps;
+    p.n_img = nb; p.H = R; p.W = R; p.Cin = w.cin; p.Cout = w.cout; p.taps = w.taps; p.stride = stride;
     p.bw = R >= 128 ? 128 : R; p.bh = 128 / p.bw;
     p.bias = w.bias; p.residual = residual;
-    const uint64_t adims[4] = {(uint64_t)w.cin, (uint64_t)R + 2, (uint64_t)R + 2, (uint64_t)nb};
-    const uint32_t abox[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, 1};
+    const uint64_t plane_w = stride == 2 ? (uint64_t)(Rin + 2) / 2 : (uint64_t)R + 2;
+    const uint64_t adims[5] = {(uint64_t)w.cin, plane_w, plane_w, (uint64_t)nb, stride == 2 ? 4u : 1u};
+    const uint32_t abox[5] = {64, (uint32_t)p.bw, (uint32_t)p.bh, 1, 1};
     const uint64_t odims[2] = {(uint64_t)w.cout, (uint64_t)nb * R * R};
     const uint32_t obox[2] = {32, 32};
     CUtensorMap *tahi, *talo, *tout;
-    MB_TRY(cached_tmap(h, &tahi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4, h->act_hi, adims, abox));
-    MB_TRY(cached_tmap(h, &talo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4, h->act_lo, adims, abox));
+    MB_TRY(cached_tmap(h, &tahi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 5, h->act_hi, adims, abox));
+    MB_TRY(cached_tmap(h, &talo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 5, h->act_lo, adims, abox));
     MB_TRY(cached_tmap(h, &tout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 2, out, odims, obox));
     const int tiles = nb * (R / p.bh) * (R / p.bw) * (w.cout / ConvTcCfg::BN);
     const int grid = tiles < h->num_sms ? tiles : h->num_sms;
@@ -940,6 +993,53 @@ static int decode_impl(mb_handle* h, const int64_t* tokens, int B, float* images
 extern "C" int mb_decode_tokens(mb_handle* h, const int64_t* tokens, int B, float* images, mb_stream stream) {
     if (!h || !tokens || !images || B <= 0) return fail(MB_ERR_INVALID, "mb_decode_tokens: bad argument");
     return decode_impl(h, tokens, B, images, (cudaStream_t)stream);
+}
+
+// ConvVQModel.encode (conv_vqgan.py:71-84): ConvEncoder (autoencoder.py:268-286) + LookupFreeQuantizer sign / index
+// (lookup_free.py:56-62).  images fp32 NCHW [B,3,H,W] -> z fp32 NCHW [B,bits,P,P] (optional), indices int64 [B,P*P] (optional)
+static int encode_impl(mb_handle* h, const float* images, int B, float* z, int64_t* indices, cudaStream_t st) {
+    if (!h->finalized[MB_TOKENIZER]) return fail(MB_ERR_STATE, "tokenizer weights not loaded (mb_set_tensor + mb_finalize)");
+    const mb_config& c = h->cfg;
+    const int P = (int)lround(sqrt((double)c.seq_len));
+    const int Rimg = P << (c.dec_num_resolutions - 1);
+    MB_TRY(ensure_dec_ws(h, B < kDecChunk ? B : kDecChunk));
+    for (int b0 = 0; b0 < B; b0 += kDecChunk) {
+        const int nb = B - b0 < kDecChunk ? B - b0 : kDecChunk;
+        float *X = h->dx, *T1 = h->dt1, *T2 = h->dt2;
+        int R = Rimg;
+        {
+            ProfScope prof(h, MB_PROF_DEC_IO, st);
+            const long long total = (long long)nb * R * R * (h->enc_c0 / 4);
+            enc_conv_in_kernel<<<(unsigned)((total + 255) / 256), 256, 27 * h->enc_c0 * sizeof(float), st>>>(
+                images + (size_t)b0 * 3 * R * R, h->enc_cin_w, X, nb, R, R, h->enc_c0);
+            CU_TRY(cudaGetLastError()); h->launches++;
+        }
+        for (auto& stg : h->enc_down) {
+            for (auto& rb : stg.blocks) MB_TRY(run_block(h, rb, X, T1, T2, nb, R, st));
+            if (stg.has_down) {
+                R /= 2;
+                MB_TRY(run_conv(h, X, T1, stg.down, nb, R, false, 0, nullptr, st, 2));   // 3x3 stride 2, SAME pad 0/1 (autoencoder.py:160,178)
+                float* t = X; X = T1; T1 = t;
+            }
+        }
+        for (auto& rb : h->enc_mid) MB_TRY(run_block(h, rb, X, T1, T2, nb, R, st));
+        MB_TRY(run_gn(h, X, h->enc_norm_out, nb, R, st));
+        {
+            ProfScope prof(h, MB_PROF_DEC_IO, st);
+            const long long npix = (long long)nb * R * R;
+            enc_conv_out_kernel<<<(unsigned)((npix + 7) / 8), 256, 0, st>>>(X, h->gn_scale, h->gn_shift, h->enc_cout_w, h->enc_cout_b,
+                                                                          z ? z + (size_t)b0 * h->bits * R * R : nullptr,
+                                                                          indices ? indices + (size_t)b0 * R * R : nullptr, nb, R * R,
+                                                                          h->enc_cl, h->bits);
+            CU_TRY(cudaGetLastError()); h->launches++;
+        }
+    }
+    return 0;
+}
+extern "C" int mb_encode(mb_handle* h, const float* images, int B, float* z, int64_t* indices, mb_stream stream) {
+    if (!h || !images || B <= 0 || (!z && !indices)) return fail(MB_ERR_INVALID, "mb_encode: bad argument");
+    if (h->bits > 32) return fail(MB_ERR_INVALID, "mb_encode: token_size %d > 32", h->bits);
+    return encode_impl(h, images, B, z, indices, (cudaStream_t)stream);
 }
 
 extern "C" int mb_postprocess_u8(mb_handle* h, const float* images, int B, uint8_t* out, mb_stream stream) {

@@ -3,6 +3,8 @@
 // A 3x3 (or 1x1) stride-1 SAME convolution over NHWC activations is a GEMM  out[pixel, cout] = sum_{tap, cin} A * W  with
 //   M = pixels (tile: 128 consecutive pixels = bh full rows, or half a row at W = 256), N = 128 output channels,
 //   K = taps x Cin consumed in chunks of 64 channels of one tap.
+// Stride-2 convolutions of the tokenizer encoder (Conv2dSame: pad 0 top/left, 1 bottom/right) read the same zero-bordered
+// input stored as four parity planes (space-to-depth of the padded image), so every tap is again a contiguous box.
 // The 1e-3-abs pixel bar against the fp32 reference rules out single-pass bf16 (8e-2 measured), so both operands are split
 // into bf16 hi + lo and every K-step issues three MMAs (hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM): ~2^-16 relative.
 //
@@ -20,10 +22,11 @@ namespace mb {
 // ------------------------------------------------------------------------------------------------ activation transform
 // in    fp32 NHWC [N, Hin, Win, C]  (Hin = H >> up)
 // scale / shift  [N][C] GroupNorm-apply coefficients or nullptr (no norm, no SiLU)
-// hi/lo bf16 [N, H+2, W+2, C], border = 0
+// hi/lo bf16 [N, H+2, W+2, C], border = 0;  planes = 1
+//       or, planes = 4 (input of a stride-2 conv): [4][N, (H+2)/2, (W+2)/2, C], plane = (yp & 1) * 2 + (xp & 1) of padded (yp, xp)
 __global__ void __launch_bounds__(256)
 act_split_kernel(const float* __restrict__ in, const float* __restrict__ scale, const float* __restrict__ shift,
-                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int N, int H, int W, int C, int up) {
+                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int N, int H, int W, int C, int up, int planes) {
     const int c8 = C >> 3;                                      // 8-channel groups per pixel
     const long long total = (long long)N * (H + 2) * (W + 2) * c8;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -62,13 +65,20 @@ act_split_kernel(const float* __restrict__ in, const float* __restrict__ scale, 
         oh = make_uint4(wh[0], wh[1], wh[2], wh[3]);
         ol = make_uint4(wl[0], wl[1], wl[2], wl[3]);
     }
-    reinterpret_cast<uint4*>(hi)[idx] = oh;
-    reinterpret_cast<uint4*>(lo)[idx] = ol;
+    long long o = idx;
+    if (planes == 4) {
+        const int Hp = (H + 2) >> 1, Wp = (W + 2) >> 1;
+        const int pl = (yp & 1) * 2 + (xp & 1);
+        o = ((((long long)pl * N + n) * Hp + (yp >> 1)) * Wp + (xp >> 1)) * c8 + cg;
+    }
+    reinterpret_cast<uint4*>(hi)[o] = oh;
+    reinterpret_cast<uint4*>(lo)[o] = ol;
 }
 
 // ------------------------------------------------------------------------------------------------ conv kernel
 struct ConvTcParams {
-    int n_img, H, W, Cin, Cout, taps;   // taps = 9 (3x3) or 1 (1x1)
+    int n_img, H, W, Cin, Cout, taps;   // H, W = OUTPUT size; taps = 9 (3x3) or 1 (1x1)
+    int stride;                         // 1, or 2 (3x3 only; input stored as 4 parity planes)
     int bw, bh;                         // pixel tile = bh rows x bw columns, bw * bh = 128
     const float* bias;                  // [Cout] or nullptr
     const float* residual;              // fp32 NHWC [n_img*H*W, Cout] or nullptr
@@ -82,11 +92,8 @@ struct ConvTcCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 + 256;
 };
 
-__device__ __forceinline__ void tma_load_4d_b(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
-    tma_load_4d(smem_dst, m, bar, c0, c1, c2, c3);
-}
-
-// tm_ahi / tm_alo : 4D maps of the padded bf16 inputs {C, W+2, H+2, N}, box {64, bw, bh, 1}
+// tm_ahi / tm_alo : 5D maps of the padded bf16 inputs {C, Wp, Hp, N, planes}, box {64, bw, bh, 1, 1}
+//                   (stride 1: Wp = W+2, planes = 1; stride 2: Wp = (Win+2)/2 = W+1, planes = 4)
 // tm_whi / tm_wlo : 2D maps of the packed weights [Cout][taps*Cin], box {64, 128}
 // tm_out          : 2D map of the fp32 output [n_img*H*W, Cout], box {32, 32}
 __global__ void __launch_bounds__(384, 1)
@@ -138,14 +145,17 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
                 const int x0 = xb * p.bw, y0 = yb * p.bh;
                 for (int kb = 0; kb < num_k; ++kb) {
                     const int tap = kb / kchunks, c0 = (kb - tap * kchunks) * C::BK;
-                    // 3x3: padded input pixel of output (y, x) under tap (dy, dx) is (y + dy, x + dx), dy, dx in 0..2;
-                    // 1x1: the centre (y + 1, x + 1)
-                    const int dy = p.taps == 9 ? tap / 3 : 1, dx = p.taps == 9 ? tap % 3 : 1;
+                    // stride 1, 3x3: padded input pixel of output (y, x) under tap (dy, dx) is (y + dy, x + dx), dy, dx in 0..2;
+                    //           1x1: the centre (y + 1, x + 1)
+                    // stride 2 (SAME pad 0 / 1): padded pixel (2y + dy + 1, 2x + dx + 1) = plane ((dy+1)&1, (dx+1)&1), cell
+                    //           (y + (dy+1)/2, x + (dx+1)/2)
+                    int dy = p.taps == 9 ? tap / 3 : 1, dx = p.taps == 9 ? tap % 3 : 1, plane = 0;
+                    if (p.stride == 2) { plane = ((dy + 1) & 1) * 2 + ((dx + 1) & 1); dy = (dy + 1) >> 1; dx = (dx + 1) >> 1; }
                     uint8_t* sb = base + stage * C::STAGE_BYTES;
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
-                    tma_load_4d(sb, &tm_ahi, &full[stage], c0, x0 + dx, y0 + dy, img);
-                    tma_load_4d(sb + C::TILE_BYTES, &tm_alo, &full[stage], c0, x0 + dx, y0 + dy, img);
+                    tma_load_5d(sb, &tm_ahi, &full[stage], c0, x0 + dx, y0 + dy, img, plane);
+                    tma_load_5d(sb + C::TILE_BYTES, &tm_alo, &full[stage], c0, x0 + dx, y0 + dy, img, plane);
                     tma_load_2d(sb + 2 * C::TILE_BYTES, &tm_whi, &full[stage], tap * p.Cin + c0, n_blk * BN);
                     tma_load_2d(sb + 3 * C::TILE_BYTES, &tm_wlo, &full[stage], tap * p.Cin + c0, n_blk * BN);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }

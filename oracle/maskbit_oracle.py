@@ -307,3 +307,46 @@ def decode_tokens(sd, tokens, num_resolutions=5, num_res_blocks=2):
     ss = int(math.sqrt(float(z.shape[1])))
     z = z.reshape(z.shape[0], ss, ss, -1).permute(0, 3, 1, 2).contiguous()
     return conv_decoder(sd, z, num_resolutions, num_res_blocks)
+
+
+# ----------------------------------------------------------------------------------------------
+# ConvVQModel.encode / forward (conv_vqgan.py:71-84,114-132, autoencoder.py:138-184,230-286, lookup_free.py:46-94)
+# ----------------------------------------------------------------------------------------------
+def conv_encoder(sd, x, num_resolutions=5, num_res_blocks=2, prefix="encoder."):
+    """ConvEncoder.forward (autoencoder.py:268-286) with sample_with_conv=True (every shipped config): conv_in (no bias),
+    per level num_res_blocks ResidualBlocks then a stride-2 3x3 Conv2dSame (pad 0 top/left, 1 bottom/right), a last
+    ResidualStage without downsampling, mid blocks, GroupNorm + SiLU + 1x1 conv_out."""
+    h = conv_same(x, sd[prefix + "conv_in.weight"])
+    for lvl in range(num_resolutions):
+        for r in range(num_res_blocks):
+            h = res_block(sd, f"{prefix}down.{lvl}.res_blocks.{r}.", h)
+        if lvl < num_resolutions - 1:
+            h = conv_same(h, sd[f"{prefix}down.{lvl}.down_conv.weight"], sd[f"{prefix}down.{lvl}.down_conv.bias"], stride=2)
+    for r in range(num_res_blocks):
+        h = res_block(sd, f"{prefix}mid.res_blocks.{r}.", h)
+    h = group_norm_silu(h, sd[prefix + "norm_out.weight"], sd[prefix + "norm_out.bias"])
+    return conv_same(h, sd[prefix + "conv_out.weight"], sd[prefix + "conv_out.bias"])
+
+
+def lfq_quantize(z):
+    """LookupFreeQuantizer.forward in eval mode (lookup_free.py:46-94): returns (z_quantized [B,C,H,W], indices [B,H,W]).
+    z_quantized = z + (sign - z), i.e. +-1 up to fp32 rounding, exactly as the reference computes it."""
+    zt = z.permute(0, 2, 3, 1).contiguous()
+    ones = torch.ones_like(zt)
+    zq = torch.where(zt > 0.0, ones, -ones)
+    idx = bits_to_indices(zq)
+    zq = zt + (zq - zt)
+    return zq.permute(0, 3, 1, 2).contiguous(), idx
+
+
+def encode(sd, x, num_resolutions=5, num_res_blocks=2):
+    """ConvVQModel.encode (conv_vqgan.py:71-84): returns (z_quantized, indices, z)."""
+    z = conv_encoder(sd, x, num_resolutions, num_res_blocks)
+    zq, idx = lfq_quantize(z)
+    return zq, idx, z
+
+
+def autoencode(sd, x, num_resolutions=5, num_res_blocks=2):
+    """ConvVQModel.forward (conv_vqgan.py:114-132): (reconstruction, indices)."""
+    zq, idx, _ = encode(sd, x, num_resolutions, num_res_blocks)
+    return conv_decoder(sd, zq, num_resolutions, num_res_blocks), idx

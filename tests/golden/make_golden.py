@@ -12,6 +12,7 @@ Fixtures written (all small enough to commit):
                       (q ~ Exp(1), g ~ Gumbel) and the reference's per-step predicted tokens
   sample_12bit.npz    BASELINE config #1: sample() B=4, 8 steps, CFG cosine: per-step tokens + pixels
   decode_12bit.npz    ConvVQModel.decode_tokens on random tokens, B=2
+  encode_12bit.npz    ConvVQModel.forward (encode -> LFQ -> decode) on seeded images, B=2: latents z, indices, reconstruction
 """
 import os
 import sys
@@ -112,11 +113,32 @@ def golden_decode(vq, bits, path):
     print(path, img.shape, float(img.min()), float(img.max()))
 
 
+def golden_encode(vq, path):
+    """BASELINE config #4 shape at B=2: images in [0,1] (data/webdataset_reader.py:83) -> encoder latents, LFQ indices, reconstruction."""
+    g = torch.Generator().manual_seed(4242)
+    # smooth-ish random images: low-resolution noise upsampled, so that latents are not all near 0
+    x = torch.nn.functional.interpolate(torch.rand((2, 3, 32, 32), generator=g), size=(256, 256), mode="bilinear", align_corners=False)
+    x = (x + 0.1 * torch.rand((2, 3, 256, 256), generator=g)).clamp(0, 1)
+    with torch.no_grad():
+        z = vq.encoder(x)
+        recon, d = vq(x)
+    np.savez_compressed(path, x_seed=np.int64(4242), z=z.numpy(), indices=d["min_encoding_indices"].numpy().astype(np.int32),
+                        recon0=recon[0].numpy(), recon_sub=recon[:, :, ::4, ::4].contiguous().numpy())
+    print(path, z.shape, float(z.abs().min()), float(z.abs().mean()))
+
+
+def golden_encode_input():
+    g = torch.Generator().manual_seed(4242)
+    x = torch.nn.functional.interpolate(torch.rand((2, 3, 32, 32), generator=g), size=(256, 256), mode="bilinear", align_corners=False)
+    return (x + 0.1 * torch.rand((2, 3, 256, 256), generator=g)).clamp(0, 1)
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     cfg, kw, vq, gen = build_reference(12)
     golden_forward(gen, 12, 4, os.path.join(HERE, "forward_12bit.npz"))
     golden_decode(vq, 12, os.path.join(HERE, "decode_12bit.npz"))
+    golden_encode(vq, os.path.join(HERE, "encode_12bit.npz"))
     golden_sample(kw, vq, gen, 2, 4, os.path.join(HERE, "select_12bit.npz"), with_logits=True)
     golden_sample(kw, vq, gen, 4, 8, os.path.join(HERE, "sample_12bit.npz"), with_logits=False)
     del vq, gen

@@ -236,6 +236,56 @@ def test_decode_batch_chunking_and_latents():
     assert tokenizer.decode_tokens(tokens[:0]).shape == (0, 3, 256, 256)   # empty batch
 
 
+def _golden_encode_input():
+    """The seeded images of tests/golden/make_golden.py::golden_encode (images in [0,1])."""
+    g = torch.Generator().manual_seed(4242)
+    x = torch.nn.functional.interpolate(torch.rand((2, 3, 32, 32), generator=g), size=(256, 256), mode="bilinear", align_corners=False)
+    return (x + 0.1 * torch.rand((2, 3, 256, 256), generator=g)).clamp(0, 1)
+
+
+def test_encode_matches_reference_golden(golden_dir):
+    """BASELINE config #4 path (tokenizer encode -> LFQ -> decode) against the reference's own outputs: latents within 1e-3,
+    tokens bit-exact wherever the reference latent is not within that tolerance of the sign boundary, reconstruction
+    within 1e-3 (the two images' tokens agree completely on this fixture, asserted)."""
+    g = np.load(os.path.join(golden_dir, "encode_12bit.npz"))
+    _, _, tokenizer, _ = models(12)
+    x = _golden_encode_input().cuda()
+    idx, z = tokenizer.tokenize(x, return_latents=True)
+    z_ref = torch.from_numpy(g["z"]).cuda()
+    idx_ref = torch.from_numpy(g["indices"].astype(np.int64)).cuda()
+    dz = (z - z_ref).abs().max().item()
+    print(f"encode: max abs latent error {dz:.3e} (|z| mean {z_ref.abs().mean().item():.3f})")
+    assert dz <= PIXEL_MAX_ABS
+    safe = (z_ref.abs() > 2e-3).all(dim=1)                       # every bit of the token is away from the sign boundary
+    assert safe.float().mean().item() > 0.9
+    assert torch.equal(idx[safe], idx_ref[safe])
+    bits = ((idx.unsqueeze(1) >> torch.arange(12, device="cuda").view(1, -1, 1, 1)) & 1).bool()
+    assert torch.equal(bits, z > 0)                              # token bit k <-> sign of latent k (lookup_free.py:56-60,126-127)
+    assert torch.equal(idx, idx_ref)
+    recon, d = tokenizer(x)
+    assert torch.equal(d["min_encoding_indices"], idx) and recon.shape == (2, 3, 256, 256)
+    e0 = (recon[0].cpu() - torch.from_numpy(g["recon0"])).abs().max().item()
+    es = (recon[:, :, ::4, ::4].cpu() - torch.from_numpy(g["recon_sub"])).abs().max().item()
+    print(f"autoencode: max abs pixel error {max(e0, es):.3e}")
+    assert e0 <= PIXEL_MAX_ABS and es <= PIXEL_MAX_ABS
+    zq, d2 = tokenizer.encode(x)
+    assert set(zq.unique().tolist()) == {-1.0, 1.0} and torch.equal(tokenizer.decode(zq), recon)
+    assert abs(d2["commitment_loss"].item() - 0.25 * ((torch.sign(z_ref) - z_ref) ** 2).mean().item()) < 1e-4
+
+
+def test_encode_batch_chunking_and_roundtrip():
+    """B above the internal 32-image chunk; encode(decode(tokens)) is a fixed map per image (each image independent)."""
+    _, _, tokenizer, _ = models(12)
+    g = torch.Generator().manual_seed(8)
+    x = torch.rand((34, 3, 256, 256), generator=g).cuda()
+    idx = tokenizer.tokenize(x)
+    for b in (0, 31, 32, 33):
+        assert torch.equal(tokenizer.tokenize(x[b:b + 1])[0], idx[b])
+    assert int(idx.min()) >= 0 and int(idx.max()) < 4096
+    with pytest.raises(ValueError):
+        tokenizer.tokenize(torch.zeros((1, 3, 128, 128)))
+
+
 def test_postprocess_uint8():
     _, _, tokenizer, _ = models(12)
     g = torch.Generator().manual_seed(6)

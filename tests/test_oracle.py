@@ -121,3 +121,26 @@ def test_sample_config1_matches_reference(golden_dir, synthetic_checkpoints):
     assert np.array_equal(torch.stack(trace).numpy(), g["tokens"].astype(np.int64))
     assert (img[0] - torch.from_numpy(g["image0"])).abs().max().item() <= 2e-5
     assert (img[:, :, ::4, ::4] - torch.from_numpy(g["image_sub"])).abs().max().item() <= 2e-5
+
+
+def golden_encode_input():
+    """The seeded images of tests/golden/make_golden.py::golden_encode (images in [0,1])."""
+    g = torch.Generator().manual_seed(4242)
+    x = torch.nn.functional.interpolate(torch.rand((2, 3, 32, 32), generator=g), size=(256, 256), mode="bilinear", align_corners=False)
+    return (x + 0.1 * torch.rand((2, 3, 256, 256), generator=g)).clamp(0, 1)
+
+
+def test_encode_matches_reference(golden_dir, synthetic_checkpoints):
+    """BASELINE config #4 path at B=2: the oracle's encoder / LFQ / decoder chain reproduces the reference's latents to 2e-5,
+    its indices exactly and its reconstruction to 2e-5."""
+    g = np.load(os.path.join(golden_dir, "encode_12bit.npz"))
+    _, sd = synthetic_checkpoints(12)
+    x = golden_encode_input()
+    zq, idx, z = O.encode(sd, x)
+    assert (z - torch.from_numpy(g["z"])).abs().max().item() <= 2e-5
+    assert np.array_equal(idx.numpy(), g["indices"].astype(np.int64))
+    assert set(zq.round().unique().tolist()) == {-1.0, 1.0}
+    recon, idx2 = O.autoencode(sd, x)
+    assert torch.equal(idx, idx2)
+    assert (recon[0] - torch.from_numpy(g["recon0"])).abs().max().item() <= 2e-5
+    assert (recon[:, :, ::4, ::4] - torch.from_numpy(g["recon_sub"])).abs().max().item() <= 2e-5
