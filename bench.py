@@ -288,6 +288,72 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ BASELINE config #4
+def run_tokenizer(args):
+    """MaskBit-Tokenizer 12-bit encode -> LFQ -> decode reconstruction (conv path isolation), one GPU.
+    A step = ConvVQModel.forward on `--batch` images (default 512).  Algorithmic work 322.09 GFLOP per image
+    (encoder 136.12 + decoder 185.97); the convs run as three bf16 MMAs per product (split operands)."""
+    import torch
+    from maskbit_b200 import build_models, load_config
+    torch.cuda.set_device(0)
+    cfg = load_config(f"maskbit_generator_{args.bits}bit")
+    tokenizer, _ = build_models(cfg, device="cuda:0")
+    B = args.batch
+    x_host = torch.rand((B, 3, 256, 256), generator=torch.Generator().manual_seed(1234)).pin_memory()
+    x_dev = x_host.cuda()
+    out_host = torch.empty((B, 256, 256, 3), dtype=torch.uint8).pin_memory()
+
+    def step(e2e):
+        x = x_host.cuda(non_blocking=True) if e2e else x_dev
+        recon, d = tokenizer(x)
+        if e2e:
+            out_host.copy_(tokenizer.postprocess_uint8(recon), non_blocking=True)
+        return d["min_encoding_indices"]
+
+    def timed(n, e2e):
+        torch.cuda.synchronize()
+        l0 = tokenizer.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            step(e2e)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), tokenizer.launch_count() - l0
+
+    for _ in range(args.warmup):
+        step(True)
+    uuid = str(torch.cuda.get_device_properties(0).uuid)
+    clocks = ClockSampler(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+    tokenizer.profile_enable(True)
+    ms, launches = timed(args.steps, False)
+    prof = tokenizer.profile_read()
+    tokenizer.profile_enable(False)
+    clk = clocks.stop()
+    ms_e2e, _ = timed(args.steps, True)
+    peaks = measured_peaks()
+    n_img = B * args.steps
+    flops_img = 136.12e9 + F_DEC.get(args.bits, 185.97e9)
+    conv_ms, conv_n = prof.get("dec_conv", (0.0, 0))
+    conv_flops = n_img * (flops_img - 0.45e9 - 0.028e9 - 0.45e9)          # minus conv_in / conv_out of both halves (CUDA-core kernels)
+    achieved = conv_flops / (conv_ms / 1000.0) / 1e12 if conv_ms else None
+    gpu_ms = sum(v[0] for v in prof.values())
+    line = {"metric": "images_per_sec", "value": n_img / (ms / 1000.0), "unit": "images/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": f"MaskBit-Tokenizer {args.bits}-bit encode->LFQ->decode reconstruction, batch={B}, 256x256 (BASELINE configs[3])",
+                       "batch": B, "images": "synthetic uniform [0,1]", "l2": "activations (GBs per layer) exceed the 126 MB L2"},
+            "e2e": {"value": n_img / (ms_e2e / 1000.0), "unit": "images/s", "h2d_bytes_per_step": B * 3 * 256 * 256 * 4,
+                    "d2h_bytes_per_step": B * 256 * 256 * 3},
+            "gpu_launches": int(launches), "clocks": clk,
+            "roofline": {"bound": "tensor", "kernel": "conv_tcgen05_kernel (3 MMAs per product)", "achieved": achieved,
+                         "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": (achieved / peaks["bf16_sustained"]) if achieved else None,
+                         "traffic": None, "peak_source": f"{peaks['source']} bf16_tflops_sustained", "launches": conv_n,
+                         "note": "algorithmic (single-pass) conv FLOPs; the tensor pipe executes 3x that"},
+            "kernel_time_share": {k: round(v[0] / gpu_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -295,7 +361,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--bits", type=int, default=12)
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--workload", default="sample", choices=["sample", "tokenizer"],
+                    help="sample: the sampling hot path (BASELINE configs[1], default); tokenizer: encode->LFQ->decode (configs[3])")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default 256; 512 for --workload tokenizer)")
     ap.add_argument("--sampling-steps", type=int, default=64)
     ap.add_argument("--skip-dead-uncond", type=int, default=1,
                     help="skip the unconditional forward on steps whose guidance scale is exactly 0.0 (bit-identical; FLOPs still "
@@ -305,6 +373,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e pass (profiling runs under ncu only)")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 512 if args.workload == "tokenizer" else 256
+    if args.workload == "tokenizer" and args.impl != "reference":
+        return run_tokenizer(args)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -224,7 +224,7 @@ struct mb_handle {
     __nv_bfloat16 *yA = nullptr, *yB = nullptr, *qkv = nullptr, *att = nullptr, *hmid = nullptr;
     float2 *stA = nullptr, *stB = nullptr;
     CUtensorMap tm_yA, tm_yB, tm_att, tm_hmid, tm_qkv_big, tm_qkv_row;
-    CUtensorMap tmo_yA, tmo_yB, tmo_qkv, tmo_hmid;   // output maps (box 64 x 32) of the same buffers
+    CUtensorMap tmo_yA, tmo_yB, tmo_qkv, tmo_hmid, tmo_att;   // output maps (box 64 x 32) of the same buffers
     // sampler workspace
     int cap_sample_B = 0;
     int64_t *tok_a = nullptr, *tok_b = nullptr, *pred_buf = nullptr, *combined = nullptr;
@@ -742,6 +742,7 @@ static int ensure_ws(mb_handle* h, int n_seq) {
     MB_TRY(make_tmap_out(&h->tmo_yB, h->yB, rows, D));
     MB_TRY(make_tmap_out(&h->tmo_qkv, h->qkv, rows, 3 * D));
     MB_TRY(make_tmap_out(&h->tmo_hmid, h->hmid, rows, h->cfg.mlp_dim));
+    MB_TRY(make_tmap_out(&h->tmo_att, h->att, rows, D));
     h->cap_seqs = n_seq; h->cap_rows = rows;
     return 0;
 }
@@ -751,15 +752,15 @@ extern "C" int mb_test_attention_trace(long long* device_buf) { g_attn_trace = d
 
 // softmax(Q K^T / 8) V for every (sequence, head): the persistent tcgen05 kernel for the 257-token grid, the generic
 // mma.sync kernel for any other sequence length
-static int run_attention(mb_handle* h, const CUtensorMap& tm_big, const CUtensorMap& tm_row, const __nv_bfloat16* qkv,
-                         __nv_bfloat16* out, int n_seq, int S, int D, int H, int num_sms, cudaStream_t st) {
+static int run_attention(mb_handle* h, const CUtensorMap& tm_big, const CUtensorMap& tm_row, const CUtensorMap& tm_out,
+                         const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_seq, int S, int D, int H, int num_sms, cudaStream_t st) {
     const float sl2 = 1.4426950408889634f / sqrtf((float)ATT_HD);
     ProfScope prof(h, MB_PROF_ATTENTION, st);
     if (S == 257) {
         AttnTcParams p;
         p.out = out; p.n_items = n_seq * H; p.H = H; p.D = D; p.sl2 = sl2; p.trace = g_attn_trace;
         const int grid = p.n_items < num_sms ? p.n_items : num_sms;
-        attention_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM_BYTES, st>>>(tm_big, tm_row, p);
+        attention_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM_BYTES, st>>>(tm_big, tm_row, tm_out, p);
     } else {
         attention_kernel<<<n_seq * H, ATT_THREADS, 2 * ATT_MAXS * ATT_LDS * 2, st>>>(qkv, out, S, D, H, sl2);
     }
@@ -788,7 +789,7 @@ static int forward_impl(mb_handle* h, const int64_t* tokens, int n_token_rows, c
         const Layer& L = h->layers[l];
         // attention block (bert.py:137-139): yB = out_proj(MHA(LN(yA))) + LN(yA)
         MB_TRY(run_linear(h, MB_PROF_GEMM_QKV, h->tm_yA, L.qkv, M, EPI_LNIN_BF16, nullptr, h->stA, nullptr, h->qkv, &h->tmo_qkv, 3 * D, st));
-        MB_TRY(run_attention(h, h->tm_qkv_big, h->tm_qkv_row, h->qkv, h->att, n_seq, h->S, D, c.heads, h->num_sms, st));
+        MB_TRY(run_attention(h, h->tm_qkv_big, h->tm_qkv_row, h->tmo_att, h->qkv, h->att, n_seq, h->S, D, c.heads, h->num_sms, st));
         MB_TRY(run_linear(h, MB_PROF_GEMM_OUT, h->tm_att, L.out, M, EPI_RES_LN_BF16_STATS, h->yA, h->stA, h->stB, h->yB, &h->tmo_yB, D, st));
         // feed-forward block (bert.py:69-70): yA = W2 gelu(W1 LN1(yB) + b1) + b2 + LN1(yB)
         MB_TRY(run_linear(h, MB_PROF_GEMM_UP, h->tm_yB, L.up, M, EPI_LNIN_GELU_BF16, nullptr, h->stB, nullptr, h->hmid, &h->tmo_hmid, c.mlp_dim, st));
@@ -1148,9 +1149,10 @@ extern "C" int mb_test_gemm(const uint16_t* A, const uint16_t* W, const float* b
 extern "C" int mb_test_attention(const uint16_t* qkv, uint16_t* out, int n_seq, int S, int D, int H, mb_stream stream) {
     MB_TRY(init_kernel_attrs());
     if (D / H != ATT_HD || S > ATT_MAXS || (S % 64) > 16) return fail(MB_ERR_INVALID, "attention shape unsupported");
-    CUtensorMap tb, tr;
+    CUtensorMap tb, tr, to;
     MB_TRY(make_tmap_bf16(&tb, qkv, (uint64_t)n_seq * S, 3 * D, 256));
     MB_TRY(make_tmap_bf16(&tr, qkv, (uint64_t)n_seq * S, 3 * D, 16));
-    return run_attention(nullptr, tb, tr, reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out),
+    MB_TRY(make_tmap_out(&to, out, (uint64_t)n_seq * S, D));
+    return run_attention(nullptr, tb, tr, to, reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out),
                          n_seq, S, D, H, test_num_sms(), (cudaStream_t)stream);
 }

@@ -20,7 +20,7 @@
 // 257 = 2*128 + 1: tensor tiles cover the 256x256 block exactly; the odd row and column never touch a padded tcgen05 tile.
 //
 // Input  qkv  bf16 [rows, 3*D] through two TMA maps (box 64x256 and box 64x16); head h at columns h*64 of each third
-// Output out  bf16 [n_seq*257, D]
+// Output out  bf16 [n_seq*257, D] (rows 0..255 of every sequence through a TMA map with box 64x32, row 256 by direct stores)
 #pragma once
 #include "attention.cuh"   // ldsm_x4, ldsm_x4_t, mma_bf16_16816
 #include "ptx.cuh"
@@ -131,7 +131,8 @@ struct AttnTcParams {
 };
 
 __global__ void __launch_bounds__(ATC_THREADS, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant__ CUtensorMap tm_row, AttnTcParams p) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant__ CUtensorMap tm_row,
+                    const __grid_constant__ CUtensorMap tm_out, AttnTcParams p) {
     constexpr int S = 257;
     extern __shared__ uint8_t atc_smem_raw[];
     const uint32_t raw = smem_u32(atc_smem_raw);
@@ -148,7 +149,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_big); tma_prefetch_desc(&tm_row); }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_big); tma_prefetch_desc(&tm_row); tma_prefetch_desc(&tm_out); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < 2; ++s) {
             mbar_init(&full[s], 1); mbar_init(&empty[s], 11);
@@ -397,7 +398,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
             const float inv = 1.0f / (sum0 + sum1 + e256);
             const float ei = e256 * inv;
             mbar_wait(&full[st], ph);                                  // (long complete) makes the TMA-written V[256] row visible
-            __nv_bfloat16* orow = p.out + ((size_t)seq * S + row) * p.D + head * 64;
+            // Output staging: this warp's 32 rows of the Q tile (S_t is complete and the class warp has finished its pass over Q:
+            // both were waited on above), 128-byte rows with the 128B swizzle, then ONE TMA store of the 32 x 64 box.
+            uint8_t* stg = base + st * ATC_STAGE_BYTES + t * (128 * 128) + quarter * 4096;
             mbar_wait(&o_full[t], ip);
             tc_fence_after();
             if (quarter == 0 && lane == 0) ATC_EV(3 + t, 3, it);
@@ -420,8 +423,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
                         b = fmaf(b, inv, bf_hi(w[j]) * ei);
                         o[j] = pack2_bf16(a, b);
                     }
-                    reinterpret_cast<uint4*>(orow)[hh * 4 + c] = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4*>(stg + lane * 128 + (((hh * 4 + c) ^ (lane & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
+            }
+            fence_async_proxy();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(&tm_out, stg, head * 64, seq * S + t * 128 + quarter * 32);
+                tma_store_commit();
+                tma_store_wait_read<0>();                              // the stage may be refilled once the store has read it
             }
             tc_fence_before();
             __syncwarp();
@@ -429,6 +439,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
             if (quarter == 0 && lane == 0) ATC_EV(3 + t, 4, it);
         }
     }
+    if (warp >= 4 && lane == 0) tma_store_wait_all<0>();
     __syncwarp();
     tc_fence_before();
     __syncthreads();
