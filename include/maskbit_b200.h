@@ -184,6 +184,8 @@ int mb_test_gemm_ex(const uint16_t* A, const uint16_t* W, const float* bias, con
 int mb_test_attention(const uint16_t* qkv, uint16_t* out, int n_seq, int S, int D, int H, mb_stream stream);
 /* builds with -DATC_TRACE=1 only: device buffer int64 [8 roles][8 events][12 items] receiving block 0's clock64 stamps */
 int mb_test_attention_trace(long long* device_buf);
+/* GEMM_TRACE builds: device buffer [4 roles][4 events][32 tiles] of clock64 stamps written by the leader CTA of pair 0 */
+int mb_test_gemm_trace(long long* device_buf);
 #ifdef __cplusplus
 }
 #endif

@@ -1123,6 +1123,8 @@ static int test_num_sms() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     return n;
 }
+static long long* g_gemm_trace = nullptr;   // GEMM_TRACE builds: device buffer [4][4][32] set by mb_test_gemm_trace
+extern "C" int mb_test_gemm_trace(long long* device_buf) { g_gemm_trace = device_buf; return 0; }
 extern "C" int mb_test_gemm_ex(const uint16_t* A, const uint16_t* W, const float* bias, const float* vec2, const uint16_t* residual,
                                const float* stats_in, float* stats_out, void* out, int M, int N, int K, int epi, int seq_in,
                                int seq_out, float inv_d, float eps, mb_stream stream) {
@@ -1138,7 +1140,7 @@ extern "C" int mb_test_gemm_ex(const uint16_t* A, const uint16_t* W, const float
     GemmParams p;
     p.M = M; p.N = N; p.K = K; p.bias = bias; p.vec2 = vec2; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = N;
     p.stats_in = reinterpret_cast<const float2*>(stats_in); p.stats_out = reinterpret_cast<float2*>(stats_out);
-    p.inv_d = inv_d; p.eps = eps; p.out = out; p.ldo = N; p.seq_in = seq_in; p.seq_out = seq_out;
+    p.inv_d = inv_d; p.eps = eps; p.out = out; p.ldo = N; p.seq_in = seq_in; p.seq_out = seq_out; p.trace = g_gemm_trace;
     return launch_gemm(nullptr, ta, tb, BN == 256 ? &tbh : nullptr, (BN == 256 && bf16_out) ? &tc : nullptr, BN, p, epi, test_num_sms(),
                        (cudaStream_t)stream);
 }

@@ -119,8 +119,6 @@ __device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
 }
 // 16-byte chunk `ch` of row `r` inside a 128B-swizzled tile of 128-byte rows
 __device__ __forceinline__ uint32_t sw128(uint32_t tile, int r, int ch) { return tile + r * 128 + ((ch ^ (r & 7)) << 4); }
-__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 struct AttnTcParams {
     __nv_bfloat16* out;   // [n_seq*257, D]

@@ -28,6 +28,33 @@
 #define GEMM_TIMING_NO_GELU 0    // timing experiments only
 #endif
 
+#ifndef GEMM_TIMING_NO_MMA
+#define GEMM_TIMING_NO_MMA 0     // timing experiments only (CTA-pair kernel): issue no MMAs, keep loads + barriers + epilogue
+#endif
+#ifndef GEMM_TIMING_NO_EPI
+#define GEMM_TIMING_NO_EPI 0     // timing experiments only (CTA-pair kernel): epilogue warps only hand the accumulator back
+#endif
+#ifndef GEMM2_ROLES_HIGH
+#define GEMM2_ROLES_HIGH 0       // CTA-pair kernel: 1 = epilogue warps 0..7, TMA / MMA / TMEM-alloc warps 8 / 9 / 10
+#endif
+#ifndef GEMM2_STAGES
+#define GEMM2_STAGES 6
+#endif
+#ifndef GEMM_TRACE
+#define GEMM_TRACE 0             // 1: the leader CTA of pair 0 records clock64 stamps per tile into GemmParams::trace
+#endif
+#if GEMM_TRACE
+#define GEMM_EV(role, ev, it, val)                                                                                 \
+    do {                                                                                                           \
+        if (blockIdx.x == 0 && p.trace && (it) < 32u) p.trace[((role) * 4 + (ev)) * 32 + (it)] = (val);            \
+    } while (0)
+#else
+#define GEMM_EV(role, ev, it, val) do {} while (0)
+#endif
+#ifndef GEMM_RES_PREFETCH
+#define GEMM_RES_PREFETCH 1      // residual epilogue: load the thread's residual-row slab before the accumulator wait
+#endif
+
 namespace mb {
 
 enum EpiMode : int {
@@ -57,6 +84,7 @@ struct GemmParams {
     void* out;                       // bf16 or fp32, row stride ldo elements
     int ldo;
     int seq_in, seq_out;             // *_SEQ: rows per sequence in A / kept rows per sequence in out
+    long long* trace = nullptr;      // GEMM_TRACE builds: [roles 4][events 4][tiles 32] clock64 stamps, else unused
 };
 
 template <int BN>
@@ -175,6 +203,18 @@ __device__ __forceinline__ void ln_row_stats(const float2* __restrict__ st, floa
 // One output row per thread.  epi_prepare runs before the accumulator wait (its loads overlap the tile's MMAs), epi_run after.
 struct EpiRow { int row; bool row_ok, store_ok; long long out_row; float rs, nmr; };
 
+// The thread's slab of the residual-stream row (COLS bf16 columns = COLS/8 16-byte words) for the residual epilogue, loaded
+// BEFORE the accumulator wait: y comes from HBM (the residual stream is larger than L2), and four dependent
+// load -> use round trips per tile inside the epilogue were what held the K=1024 out-projection at 47 % tensor-pipe time.
+template <int COLS>
+struct ResSlab { uint4 v[COLS / 8]; };
+template <int COLS>
+__device__ __forceinline__ void epi_load_residual(const GemmParams& p, const EpiRow& er, int col0, ResSlab<COLS>& s) {
+    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)(er.row_ok ? er.row : 0) * p.ldr + col0);
+#pragma unroll
+    for (int i = 0; i < COLS / 8; ++i) s.v[i] = __ldg(rp + i);
+}
+
 template <int EPI>
 __device__ __forceinline__ EpiRow epi_prepare(const GemmParams& p, int row) {
     constexpr bool kLnIn = EPI == EPI_LNIN_BF16 || EPI == EPI_LNIN_GELU_BF16 || EPI == EPI_LNIN_GELU_BF16_STATS || EPI == EPI_LNIN_F32_SEQ;
@@ -207,9 +247,13 @@ struct EpiStage {
 
 // taddr: TMEM address of this warp's lane quarter at column 0 of the accumulator tile; the warp handles columns
 // [part * BN/NSPLIT, (part+1) * BN/NSPLIT) of the BN-wide tile n_blk.  kTma: bf16 output through smem + cp.async.bulk.tensor store.
-template <int BN, int EPI, bool kTma = false, int NSPLIT = 2>
+// svec: the tile's per-column vectors staged in shared memory ([BN] bias | [BN] vec2), or nullptr to read them from global.
+// With ~225 KB of the SM's 228 KB carved out as shared memory there is no L1 left: every __ldg of bias / u / gamma is an L2
+// round trip issued after the accumulator wait, and those round trips (not arithmetic) were most of the epilogue's time.
+template <int BN, int EPI, bool kTma = false, int NSPLIT = 2, bool kPre = false, bool kSV = false>
 __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, uint32_t taddr, int n_blk, int half,
-                                        EpiStage stg = EpiStage{nullptr, nullptr, 0}) {
+                                        EpiStage stg = EpiStage{nullptr, nullptr, 0}, const uint4* res = nullptr,
+                                        const float* svec = nullptr) {
     constexpr bool kLnIn = EPI == EPI_LNIN_BF16 || EPI == EPI_LNIN_GELU_BF16 || EPI == EPI_LNIN_GELU_BF16_STATS || EPI == EPI_LNIN_F32_SEQ;
     constexpr bool kGelu = EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_F32 || EPI == EPI_LNIN_GELU_BF16 || EPI == EPI_LNIN_GELU_BF16_STATS;
     constexpr bool kStats = EPI == EPI_RES_LN_BF16_STATS || EPI == EPI_LNIN_GELU_BF16_STATS;
@@ -221,8 +265,7 @@ __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, u
     const long long out_row = er.out_row;
     const float rs = er.rs, nmr = er.nmr;
     float st_sum = 0.f, st_sq = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < COLS_PER_WARP; c += 32) {
+    auto chunk = [&](const int c) {
         const int col0 = half * COLS_PER_WARP + c;
         uint32_t v[32];
         tmem_ld_32x32(taddr + col0, v);
@@ -231,9 +274,10 @@ __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, u
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+            const float4 b4 = kSV ? *reinterpret_cast<const float4*>(svec + col0 + j) : __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
             if (kLnIn) {   // rstd*acc + (-mean*rstd)*u + c
-                const float4 u4 = __ldg(reinterpret_cast<const float4*>(p.vec2 + n0 + j));
+                const float4 u4 = kSV ? *reinterpret_cast<const float4*>(svec + BN + col0 + j)
+                                      : __ldg(reinterpret_cast<const float4*>(p.vec2 + n0 + j));
                 f[j + 0] = fmaf(rs, __uint_as_float(v[j + 0]), fmaf(nmr, u4.x, b4.x));
                 f[j + 1] = fmaf(rs, __uint_as_float(v[j + 1]), fmaf(nmr, u4.y, b4.y));
                 f[j + 2] = fmaf(rs, __uint_as_float(v[j + 2]), fmaf(nmr, u4.z, b4.z));
@@ -254,11 +298,13 @@ __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, u
                 const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + n0);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const uint4 r4 = __ldg(rp + j);
+                    const uint4 r4 = kPre ? res[(c >> 3) + j] : __ldg(rp + j);
                     const uint32_t w[4] = {r4.x, r4.y, r4.z, r4.w};
                     if (EPI == EPI_RES_LN_BF16_STATS) {   // + ((y - mean) * rstd) * gamma   (beta is folded into p.bias)
-                        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.vec2 + n0 + j * 8));
-                        const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.vec2 + n0 + j * 8 + 4));
+                        const float4 g0 = kSV ? *reinterpret_cast<const float4*>(svec + BN + col0 + j * 8)
+                                              : __ldg(reinterpret_cast<const float4*>(p.vec2 + n0 + j * 8));
+                        const float4 g1 = kSV ? *reinterpret_cast<const float4*>(svec + BN + col0 + j * 8 + 4)
+                                              : __ldg(reinterpret_cast<const float4*>(p.vec2 + n0 + j * 8 + 4));
                         const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
                         for (int t = 0; t < 4; ++t) {
@@ -317,6 +363,13 @@ __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, u
 #pragma unroll
             for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
         }
+    };
+    if constexpr (kPre) {   // prefetched slab: indices must be compile-time constants to stay in registers
+#pragma unroll
+        for (int c = 0; c < COLS_PER_WARP; c += 32) chunk(c);
+    } else {
+#pragma unroll 1
+        for (int c = 0; c < COLS_PER_WARP; c += 32) chunk(c);
     }
     if (kStats && row_ok) {   // slot = 64-column block index of the warp's first column; a wider warp slab zeroes the slots it spans
         float2* so = p.stats_out + (size_t)row * LN_PARTIALS + (n_blk * BN + half * COLS_PER_WARP) / 64;
@@ -436,7 +489,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 //   tcgen05.commit multicasts the "stage consumed" / "accumulator ready" arrivals to both CTAs; the epilogue warps of both
 //   CTAs release the accumulator stage on the leader's tmem_empty barrier.
 struct Gemm2Cfg {
-    static constexpr int BM = 256, BN = 256, BK = 64, STAGES = 6;
+    static constexpr int BM = 256, BN = 256, BK = 64, STAGES = GEMM2_STAGES;
     // 4 TMEM lane quarters x 2 column halves.  16 warps (4 x 4, 5 stages to make room for their staging) measured SLOWER on
     // every GEMM (QKV 1435 -> 1249, up 1272 -> 1146 TFLOP/s): the extra warps and the lost stage cost more than the added
     // epilogue parallelism buys.
@@ -445,7 +498,13 @@ struct Gemm2Cfg {
     static constexpr int A_BYTES = 128 * BK * 2;      // per CTA
     static constexpr int B_BYTES = 128 * BK * 2;      // per CTA (half of the 256 weight rows)
     static constexpr int STG_BYTES = EPI_WARPS * 4096; // output staging: per epilogue warp 32 rows x 128 B
-    static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + STG_BYTES + 1024 + 256;
+    static constexpr int VEC_BYTES = 2 * BN * 4;       // the tile's per-column epilogue vectors: [BN] bias | [BN] vec2
+    static constexpr int BAR_BYTES = 192;              // 2*STAGES + 4 mbarriers + the TMEM base slot
+    // The dynamic shared-memory window is 1024-byte aligned (declared so, and checked at kernel entry): no alignment slack,
+    // which is what leaves room for VEC_BYTES next to six pipeline stages (232 448 B limit).
+    static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + STG_BYTES + VEC_BYTES + BAR_BYTES;
+    static_assert(SMEM_BYTES <= 232448, "CTA-pair GEMM shared memory over the 227 KB limit");
+    static_assert((2 * STAGES + 4) * 8 + 4 <= BAR_BYTES, "barrier area too small");
 };
 // bf16-output epilogues of the CTA-pair kernel go through shared memory and TMA stores
 #ifndef GEMM2_DIRECT256
@@ -463,13 +522,14 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
     using C = Gemm2Cfg;
     constexpr int BN = C::BN, BK = C::BK, STAGES = C::STAGES;
     constexpr bool kTma = gemm2_tma_store(EPI);
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t raw = smem_u32(smem_raw);
-    uint8_t* base = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* base = smem_raw;
+    if (smem_u32(base) & 1023u) asm volatile("trap;");   // 128B-swizzle atoms need the 1024-byte alignment declared above
     uint8_t* smem_a = base;
     uint8_t* smem_b = base + STAGES * C::A_BYTES;
     uint8_t* smem_stg = base + STAGES * (C::A_BYTES + C::B_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + C::STG_BYTES);
+    float* smem_vec = reinterpret_cast<float*>(smem_stg + C::STG_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + C::STG_BYTES + C::VEC_BYTES);
     uint64_t* full = bars;                          // used in the leader CTA only
     uint64_t* empty = bars + STAGES;                // per CTA, arrived by the leader's multicast commit
     uint64_t* tmem_full = bars + 2 * STAGES;        // per CTA, arrived by the leader's multicast commit
@@ -477,35 +537,51 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Warp roles.  The SM's warp schedulers favour the highest warp id among eligible warps, so with GEMM2_ROLES_HIGH the
+    // single-thread TMA / MMA issuers sit above the eight epilogue warps instead of below them.
+    constexpr int W_EPI0 = GEMM2_ROLES_HIGH ? 0 : 4, W_PROD = GEMM2_ROLES_HIGH ? 8 : 0, W_MMA = GEMM2_ROLES_HIGH ? 9 : 1,
+                  W_ALLOC = GEMM2_ROLES_HIGH ? 10 : 2;
+    const bool is_epi = warp >= W_EPI0 && warp < W_EPI0 + C::EPI_WARPS;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
     const int num_m = (p.M + C::BM - 1) / C::BM, num_n = p.N / BN;
     const int num_tiles = num_m * num_n, num_k = p.K / BK;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == W_PROD && lane == 0) {
         tma_prefetch_desc(&tm_a);
         tma_prefetch_desc(&tm_b);
         if (kTma) tma_prefetch_desc(&tm_c);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == W_MMA && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 2 * C::EPI_WARPS); }
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc_2sm<512>(tmem_slot);
+    if (warp == W_ALLOC) tmem_alloc_2sm<512>(tmem_slot);
     tc_fence_before();
     cluster_sync_all();                              // barriers of both CTAs initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == W_PROD) {
         if (lane == 0) {  // ---------------- TMA producer (each CTA: its 128 A rows, its 128 of the 256 B rows)
             int stage = 0; uint32_t phase = 0;
-            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+            uint32_t it = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
                 const int m_blk = tile / num_n, n_blk = tile % num_n;
+#if GEMM_TRACE
+                long long empty_wait = 0;
+#endif
                 for (int kb = 0; kb < num_k; ++kb) {
+#if GEMM_TRACE
+                    const long long t0 = clock64();
+#endif
                     mbar_wait(&empty[stage], phase ^ 1);
+#if GEMM_TRACE
+                    empty_wait += clock64() - t0;
+                    if (kb == num_k - 1) { GEMM_EV(2, 0, it, empty_wait); GEMM_EV(2, 1, it, clock64()); }
+#endif
                     if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (C::A_BYTES + C::B_BYTES));
                     const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
                     tma_load_2d_2sm(smem_a + stage * C::A_BYTES, &tm_a, bar, kb * BK, m_blk * C::BM + (int)rank * 128);
@@ -514,51 +590,87 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == W_MMA) {
         if (lane == 0 && leader) {  // ---------------- MMA issuer (leader CTA only)
             constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, 256, BN);
             int stage = 0; uint32_t phase = 0; uint32_t it = 0;
             for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
                 const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+                GEMM_EV(0, 0, it, clock64());
                 mbar_wait(&tmem_empty[as], aphase ^ 1);
                 tc_fence_after();
+                GEMM_EV(0, 1, it, clock64());
                 const uint32_t d_tmem = tmem_base + as * BN;
+#if GEMM_TRACE
+                long long full_wait = 0;
+#endif
                 for (int kb = 0; kb < num_k; ++kb) {
+#if GEMM_TRACE
+                    const long long t0 = clock64();
+#endif
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
+#if GEMM_TRACE
+                    full_wait += clock64() - t0;
+#endif
                     const uint64_t a_desc = make_sdesc_k128(smem_u32(smem_a + stage * C::A_BYTES));
                     const uint64_t b_desc = make_sdesc_k128(smem_u32(smem_b + stage * C::B_BYTES));
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
-                        umma_f16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                        if (!GEMM_TIMING_NO_MMA) umma_f16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
                     umma_commit_2sm(&empty[stage], 3);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit_2sm(&tmem_full[as], 3);
+#if GEMM_TRACE
+                GEMM_EV(0, 2, it, full_wait);
+                GEMM_EV(0, 3, it, clock64());
+#endif
             }
         }
-    } else if (warp >= 4) {  // ---------------- epilogue: each CTA its own 128 rows; warp = (lane quarter, 64-column quarter)
-        const int quarter = warp & 3, half = (warp - 4) >> 2;
+    } else if (is_epi) {  // ---------------- epilogue: each CTA its own 128 rows; warp = (lane quarter, 128-column half)
+        const int ew = warp - W_EPI0, quarter = warp & 3, half = ew >> 2;
+        // Per-column vectors of the tile -> shared memory, one float2 per epilogue thread (threads 0..127 bias, 128..255 vec2).
+        // The global load for tile i+1 is issued before tile i's epilogue runs and parked in a register pair.
+        const int e = threadIdx.x - W_EPI0 * 32;
+        const float* vsrc = e < BN / 2 ? p.bias : p.vec2;
+        const int vcol = 2 * (e & (BN / 2 - 1));
+        float2 vreg = make_float2(0.f, 0.f);
+        if (pair < num_tiles && vsrc) vreg = __ldg(reinterpret_cast<const float2*>(vsrc + (pair % num_n) * BN + vcol));
         uint32_t it = 0;
         for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
             const int m_blk = tile / num_n, n_blk = tile % num_n;
             const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+            named_bar_sync(1, C::EPI_WARPS * 32);                       // every warp has finished reading the previous tile's vectors
+            reinterpret_cast<float2*>(smem_vec)[e] = vreg;
+            named_bar_sync(2, C::EPI_WARPS * 32);
+            if (tile + num_pairs < num_tiles && vsrc)
+                vreg = __ldg(reinterpret_cast<const float2*>(vsrc + ((tile + num_pairs) % num_n) * BN + vcol));
             const int row0 = m_blk * C::BM + (int)rank * 128 + quarter * 32;
             const EpiRow er = epi_prepare<EPI>(p, row0 + lane);
+            constexpr int CPW = BN / (C::EPI_WARPS / 4);
+            constexpr bool kPre = GEMM_RES_PREFETCH && EPI == EPI_RES_LN_BF16_STATS;
+            ResSlab<kPre ? CPW : 8> slab;
+            if constexpr (kPre) epi_load_residual<CPW>(p, er, n_blk * BN + half * CPW, slab);
+            if (ew == 0 && lane == 0) GEMM_EV(1, 0, it, clock64());
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
-            epi_run<BN, EPI, kTma, C::EPI_WARPS / 4>(p, er, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN, n_blk, half,
-                                                     EpiStage{smem_stg + (warp - 4) * 4096, &tm_c, row0});
+            if (ew == 0 && lane == 0) GEMM_EV(1, 1, it, clock64());
+            if (!GEMM_TIMING_NO_EPI)
+            epi_run<BN, EPI, kTma, C::EPI_WARPS / 4, kPre, true>(p, er, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN,
+                                                                 n_blk, half, EpiStage{smem_stg + ew * 4096, &tm_c, row0}, slab.v,
+                                                                 smem_vec);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0));
+            if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tmem_empty[as]), 0));
+            if (ew == 0 && lane == 0) GEMM_EV(1, 2, it, clock64());
         }
         if (kTma && lane == 0) tma_store_wait_all<0>();   // bulk stores complete before the CTA retires its smem
     }
     __syncwarp();
     tc_fence_before();
     cluster_sync_all();                              // the leader's MMAs write the peer's TMEM: both done before dealloc
-    if (warp == 2) {
+    if (warp == W_ALLOC) {
         tc_fence_after();
         tmem_dealloc_2sm<512>(tmem_base);
     }
