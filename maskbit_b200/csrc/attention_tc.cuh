@@ -96,20 +96,11 @@ __device__ __forceinline__ float fast_exp2(float x) {   // MUFU.EX2; arguments h
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// packed fp32 pairs (FFMA2 / FADD2 on sm_100): one issue slot for two elements
-__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
-    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
-        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
-        "mov.b64 {%0, %1}, rd;\n\t}"
-        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
-}
-__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
-    asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
-        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-        "add.rn.f32x2 rd, ra, rb;\n\t"
-        "mov.b64 {%0, %1}, rd;\n\t}"
-        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+// three-input maximum (FMNMX3 on sm_100): the row-max pass needs one instruction per two scores
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
 }
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
@@ -346,11 +337,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
             for (int c = 0; c < 8; c += 2) {
                 tmem_ld_32x32(treg + (c + 1) * 32, vb);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(va[j]));
+                for (int j = 0; j < 32; j += 2) m4[(j >> 1) & 3] = fmax3(m4[(j >> 1) & 3], __uint_as_float(va[j]), __uint_as_float(va[j + 1]));
                 tmem_ld_wait();
                 tmem_ld_32x32(treg + ((c + 2) & 7) * 32, va);      // wraps to chunk 0: first chunk of pass 2
 #pragma unroll
-                for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(vb[j]));
+                for (int j = 0; j < 32; j += 2) m4[(j >> 1) & 3] = fmax3(m4[(j >> 1) & 3], __uint_as_float(vb[j]), __uint_as_float(vb[j + 1]));
                 tmem_ld_wait();
             }
             mbar_wait(&cls_ready[st], ph);

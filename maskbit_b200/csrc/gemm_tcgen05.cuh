@@ -28,6 +28,9 @@
 #define GEMM_TIMING_NO_GELU 0    // timing experiments only
 #endif
 
+#ifndef GEMM_TIMING_NO_STATS
+#define GEMM_TIMING_NO_STATS 0   // timing experiments only: skip the row-statistics stores of the STATS epilogues
+#endif
 #ifndef GEMM_TIMING_NO_MMA
 #define GEMM_TIMING_NO_MMA 0     // timing experiments only (CTA-pair kernel): issue no MMAs, keep loads + barriers + epilogue
 #endif
@@ -142,25 +145,27 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
         : "=f"(s0), "=f"(s1) : "f"(x0), "f"(x1), "f"(-0.72134752044448170f));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(s0));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(s1));
-    const float r0 = fmaxf(x0, 0.f), r1 = fmaxf(x1, 0.f);
-    // h = q * e ; out = relu(x) - |x| * h
-    asm("{\n\t.reg .b64 rq, re, ra, rr, rd;\n\t"
-        "mov.b64 rq, {%2, %3};\n\tmov.b64 re, {%4, %5};\n\tmov.b64 ra, {%6, %7};\n\tmov.b64 rr, {%8, %9};\n\t"
-        "mul.rn.f32x2 rd, rq, re;\n\tfma.rn.f32x2 rd, ra, rd, rr;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-        : "=f"(h0), "=f"(h1) : "f"(q0), "f"(q1), "f"(e0), "f"(e1), "f"(-a0), "f"(-a1), "f"(r0), "f"(r1));
+    // hm = 0.5 - q * e  (= Phi(|x|) - 0.5) ; out = 0.5 x + |x| * hm      (x Phi(x) = x/2 + |x| (Phi(|x|) - 1/2))
+    asm("{\n\t.reg .b64 rq, re, ra, rx, rh, rd;\n\t"
+        "mov.b64 rq, {%2, %3};\n\tmov.b64 re, {%4, %5};\n\tmov.b64 ra, {%6, %7};\n\tmov.b64 rx, {%8, %9};\n\tmov.b64 rh, {%10, %10};\n\t"
+        "fma.rn.f32x2 rd, rq, re, rh;\n\tmul.rn.f32x2 rd, ra, rd;\n\tfma.rn.f32x2 rd, rx, rh, rd;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(h0), "=f"(h1) : "f"(-q0), "f"(-q1), "f"(e0), "f"(e1), "f"(a0), "f"(a1), "f"(x0), "f"(x1), "f"(0.5f));
     x0 = h0; x1 = h1;
 }
 
 // The same two GELUs without the MUFU pipe: Phi(x) - 0.5 = x * Q(x^2), Q a degree-9 least-squares polynomial on x^2 <= 4.5^2
-// (|x| clamped beyond: Phi(4.5) = 1 - 3.4e-6); |gelu error| <= 5e-5 at |x| ~ 4.5 and ~1e-5 elsewhere, far below the bf16
+// (Phi saturated to 0 / 1 beyond: Phi(4.5) = 1 - 3.4e-6); |gelu error| <= 5e-5 at |x| ~ 4.5 and ~1e-5 elsewhere, far below the bf16
 // rounding of the stored value.  The GELU epilogue alternates the two forms pair by pair: with erf on the MUFU form alone
 // the special-function pipe (16 ops / clk / SM, two per element) is as busy as the tensor pipe over a 128 x 256 x 1024 tile.
 __device__ __forceinline__ void gelu_poly2(float& x0, float& x1) {
-    constexpr float L = 4.5f;
-    const float c0 = fminf(fmaxf(x0, -L), L), c1 = fminf(fmaxf(x1, -L), L);
+    // t = min(x^2, 4.5^2): beyond the fitted range x Q(t) is linear in x with slope Q(4.5^2) = (0.5 - 3.4e-6) / 4.5, so
+    // 0.5 + x Q(t) leaves [0, 1] there and the saturating FMA returns Phi = 0 / 1 -- no clamp of x itself.
+    float t0, t1;
+    fmul2(t0, t1, x0, x1, x0, x1);
+    t0 = fminf(t0, 20.25f); t1 = fminf(t1, 20.25f);
     float q0, q1;
-    asm("{\n\t.reg .b64 rt, rq, rk, rc;\n\t"
-        "mov.b64 rc, {%2, %3};\n\tmul.rn.f32x2 rt, rc, rc;\n\t"                 // t = clamp(x)^2
+    asm("{\n\t.reg .b64 rt, rq, rk;\n\t"
+        "mov.b64 rt, {%2, %3};\n\t"
         "mov.b64 rq, {%4, %4};\n\tmov.b64 rk, {%5, %5};\n\tfma.rn.f32x2 rq, rq, rt, rk;\n\t"
         "mov.b64 rk, {%6, %6};\n\tfma.rn.f32x2 rq, rq, rt, rk;\n\t"
         "mov.b64 rk, {%7, %7};\n\tfma.rn.f32x2 rq, rq, rt, rk;\n\t"
@@ -170,14 +175,12 @@ __device__ __forceinline__ void gelu_poly2(float& x0, float& x1) {
         "mov.b64 rk, {%11, %11};\n\tfma.rn.f32x2 rq, rq, rt, rk;\n\t"
         "mov.b64 rk, {%12, %12};\n\tfma.rn.f32x2 rq, rq, rt, rk;\n\t"
         "mov.b64 rk, {%13, %13};\n\tfma.rn.f32x2 rq, rq, rt, rk;\n\t"
-        "mul.rn.f32x2 rq, rq, rc;\n\t"                                             // Phi - 0.5 = clamp(x) * Q
         "mov.b64 {%0, %1}, rq;\n\t}"
         : "=f"(q0), "=f"(q1)
-        : "f"(c0), "f"(c1), "f"(-1.334576828e-12f), "f"(1.631205285e-10f), "f"(-8.910449133e-09f), "f"(2.891752189e-07f),
+        : "f"(t0), "f"(t1), "f"(-1.334576828e-12f), "f"(1.631205285e-10f), "f"(-8.910449133e-09f), "f"(2.891752189e-07f),
           "f"(-6.269251990e-06f), "f"(9.702424500e-05f), "f"(-1.118151080e-03f), "f"(9.819429864e-03f), "f"(-6.631637927e-02f),
           "f"(3.988728748e-01f));
-    x0 = fmaf(x0, q0, 0.5f * x0);
-    x1 = fmaf(x1, q1, 0.5f * x1);
+    fmul2(x0, x1, x0, x1, __saturatef(fmaf(x0, q0, 0.5f)), __saturatef(fmaf(x1, q1, 0.5f)));     // x * Phi(x)
 }
 
 __device__ __forceinline__ void st_global_v8(void* ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
@@ -210,9 +213,14 @@ template <int COLS>
 struct ResSlab { uint4 v[COLS / 8]; };
 template <int COLS>
 __device__ __forceinline__ void epi_load_residual(const GemmParams& p, const EpiRow& er, int col0, ResSlab<COLS>& s) {
-    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)(er.row_ok ? er.row : 0) * p.ldr + col0);
+    // 256-bit loads: every lane takes whole 32-byte sectors of its own row (a 128-bit load per lane fetches each sector twice)
+    const __nv_bfloat16* rp = p.residual + (size_t)(er.row_ok ? er.row : 0) * p.ldr + col0;
 #pragma unroll
-    for (int i = 0; i < COLS / 8; ++i) s.v[i] = __ldg(rp + i);
+    for (int i = 0; i < COLS / 16; ++i)
+        asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(s.v[2 * i].x), "=r"(s.v[2 * i].y), "=r"(s.v[2 * i].z), "=r"(s.v[2 * i].w), "=r"(s.v[2 * i + 1].x),
+                       "=r"(s.v[2 * i + 1].y), "=r"(s.v[2 * i + 1].z), "=r"(s.v[2 * i + 1].w)
+                     : "l"(rp + 16 * i));
 }
 
 template <int EPI>
@@ -264,7 +272,7 @@ __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, u
     const bool row_ok = er.row_ok, store_ok = er.store_ok;
     const long long out_row = er.out_row;
     const float rs = er.rs, nmr = er.nmr;
-    float st_sum = 0.f, st_sq = 0.f;
+    float st_sum = 0.f, st_sq = 0.f, st_sum1 = 0.f, st_sq1 = 0.f;   // even / odd column partial sums (packed pairs)
     auto chunk = [&](const int c) {
         const int col0 = half * COLS_PER_WARP + c;
         uint32_t v[32];
@@ -275,18 +283,17 @@ __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, u
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
             const float4 b4 = kSV ? *reinterpret_cast<const float4*>(svec + col0 + j) : __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-            if (kLnIn) {   // rstd*acc + (-mean*rstd)*u + c
+            if (kLnIn) {   // rstd*acc + (-mean*rstd)*u + c, on packed pairs
                 const float4 u4 = kSV ? *reinterpret_cast<const float4*>(svec + BN + col0 + j)
                                       : __ldg(reinterpret_cast<const float4*>(p.vec2 + n0 + j));
-                f[j + 0] = fmaf(rs, __uint_as_float(v[j + 0]), fmaf(nmr, u4.x, b4.x));
-                f[j + 1] = fmaf(rs, __uint_as_float(v[j + 1]), fmaf(nmr, u4.y, b4.y));
-                f[j + 2] = fmaf(rs, __uint_as_float(v[j + 2]), fmaf(nmr, u4.z, b4.z));
-                f[j + 3] = fmaf(rs, __uint_as_float(v[j + 3]), fmaf(nmr, u4.w, b4.w));
+                float t0, t1, t2, t3;
+                ffma2(t0, t1, nmr, nmr, u4.x, u4.y, b4.x, b4.y);
+                ffma2(t2, t3, nmr, nmr, u4.z, u4.w, b4.z, b4.w);
+                ffma2(f[j + 0], f[j + 1], rs, rs, __uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]), t0, t1);
+                ffma2(f[j + 2], f[j + 3], rs, rs, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]), t2, t3);
             } else {
-                f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
-                f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-                f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
-                f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+                fadd2(f[j + 0], f[j + 1], __uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]), b4.x, b4.y);
+                fadd2(f[j + 2], f[j + 3], __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]), b4.z, b4.w);
             }
         }
         if (kGelu && !GEMM_TIMING_NO_GELU) {
@@ -308,8 +315,9 @@ __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, u
                         const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
                         for (int t = 0; t < 4; ++t) {
-                            f[j * 8 + 2 * t + 0] = fmaf(fmaf(__uint_as_float(w[t] << 16), rs, nmr), g[2 * t], f[j * 8 + 2 * t + 0]);
-                            f[j * 8 + 2 * t + 1] = fmaf(fmaf(__uint_as_float(w[t] & 0xffff0000u), rs, nmr), g[2 * t + 1], f[j * 8 + 2 * t + 1]);
+                            float r0, r1;
+                            ffma2(r0, r1, __uint_as_float(w[t] << 16), __uint_as_float(w[t] & 0xffff0000u), rs, rs, nmr, nmr);
+                            ffma2(f[j * 8 + 2 * t], f[j * 8 + 2 * t + 1], r0, r1, g[2 * t], g[2 * t + 1], f[j * 8 + 2 * t], f[j * 8 + 2 * t + 1]);
                         }
                     } else {
 #pragma unroll
@@ -329,8 +337,8 @@ __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, u
                 w[j] = *reinterpret_cast<uint32_t*>(&h);
                 if (kStats) {   // statistics of the values as stored (bf16-rounded): the consumer normalises those
                     const float a = __uint_as_float(w[j] << 16), b = __uint_as_float(w[j] & 0xffff0000u);
-                    st_sum += a + b;
-                    st_sq = fmaf(a, a, fmaf(b, b, st_sq));
+                    fadd2(st_sum, st_sum1, st_sum, st_sum1, a, b);
+                    ffma2(st_sq, st_sq1, a, b, a, b, st_sq, st_sq1);
                 }
             }
             if (kTma) {
@@ -371,9 +379,9 @@ __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, u
 #pragma unroll 1
         for (int c = 0; c < COLS_PER_WARP; c += 32) chunk(c);
     }
-    if (kStats && row_ok) {   // slot = 64-column block index of the warp's first column; a wider warp slab zeroes the slots it spans
+    if (kStats && row_ok && !GEMM_TIMING_NO_STATS) {   // slot = 64-column block index of the warp's first column; a wider warp slab zeroes the slots it spans
         float2* so = p.stats_out + (size_t)row * LN_PARTIALS + (n_blk * BN + half * COLS_PER_WARP) / 64;
-        so[0] = make_float2(st_sum, st_sq);
+        so[0] = make_float2(st_sum + st_sum1, st_sq + st_sq1);
 #pragma unroll
         for (int i = 1; i < COLS_PER_WARP / 64; ++i) so[i] = make_float2(0.f, 0.f);
     }

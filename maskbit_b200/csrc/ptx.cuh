@@ -29,6 +29,29 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// packed fp32 pairs (FFMA2 / FADD2 on sm_100): one issue slot for two elements
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
+__device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
 // named barriers (ids 1..15; id 0 is __syncthreads) among a subset of the CTA's warps
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }

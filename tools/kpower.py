@@ -79,6 +79,7 @@ def main():
     ap.add_argument("--seqs", type=int, default=512)
     ap.add_argument("--seconds", type=float, default=3.0)
     ap.add_argument("--only", default="")
+    ap.add_argument("--shapes", default="", help="extra GEMM rows: name:N:K:epi,name:N:K:epi,...")
     a = ap.parse_args()
     L = _lib.lib()
     st = _lib.current_stream()
@@ -107,6 +108,9 @@ def main():
     gemm("gemm_out", 1024, 1024, 7)
     gemm("gemm_up", 4096, 1024, 6)
     gemm("gemm_down", 1024, 4096, 7)
+    for spec in filter(None, a.shapes.split(",")):
+        nm, n_, k_, e_ = spec.split(":")
+        gemm(nm, int(n_), int(k_), int(e_))
     if not a.only or a.only in "attention":
         qkv = torch.randn((M, 3072), device="cuda", generator=g).to(torch.bfloat16)
         out = torch.empty((M, 1024), dtype=torch.bfloat16, device="cuda")
@@ -128,7 +132,7 @@ def main():
     total = 0.0
     for name, ms, rate, w, mhz in rows:
         j = w * ms / 1e3
-        if not name.startswith("cublas"):
+        if name in ("gemm_qkv", "gemm_out", "gemm_up", "gemm_down", "attention"):
             total += j
         print(f"{name:18s} {ms:8.4f} ms  {rate:8.1f} TFLOP/s  {w:7.1f} W  {mhz:6.0f} MHz  {j:7.4f} J/launch")
     print(f"sum over one layer (512 sequences): {total:.3f} J; x24 layers = {24 * total:.1f} J per 512-sequence forward")
