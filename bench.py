@@ -53,6 +53,39 @@ def measured_peaks():
     return dict(bf16_sustained=1400.0, bf16_burst=1590.0, hbm=6650.0, source="fallback")
 
 
+def ncu_traffic(kind):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel class, from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by profiles/summarize.py traffic); None when no capture is committed."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.isfile(path):
+        return None
+    with open(path) as f:
+        return json.load(f).get(kind, {}).get("dram_bytes_per_launch")
+
+
+def library_sustained_tflops(torch, m, n, k, seconds=2.0):
+    a = torch.randn((m, k), device="cuda").to(torch.bfloat16)
+    w = torch.randn((n, k), device="cuda").to(torch.bfloat16)
+    o = torch.empty((m, n), dtype=torch.bfloat16, device="cuda")
+    torch.cuda.synchronize()
+    t_end, half = time.perf_counter() + seconds, time.perf_counter() + seconds / 2
+    ms, n_it = 0.0, 0
+    while time.perf_counter() < t_end:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            torch.matmul(a, w.t(), out=o)
+        e1.record()
+        torch.cuda.synchronize()
+        if time.perf_counter() >= half:
+            ms += e0.elapsed_time(e1)
+            n_it += 20
+    if not n_it:
+        return None
+    return {"what": f"cuBLASLt bf16 [{m},{k}]x[{n},{k}]^T, no epilogue, sustained {seconds:.0f} s loop, random normal operands",
+            "tflops": 2.0 * m * n * k / (ms / n_it) / 1e9}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -268,9 +301,10 @@ def run_b200(args):
                     "ms_per_step": ms_e2e / args.steps, "wall_s": wall_e2e},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel<256,EPI_BIAS_GELU_BF16> (MLP up GEMM)",
+            "roofline": {"bound": "tensor", "kernel": "gemm2_bf16_tcgen05_kernel<EPI_LNIN_GELU_BF16> (MLP up GEMM: LayerNorm-in + bias + GELU epilogue)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": None, "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+                         "traffic": ncu_traffic("gemm_up"),
+                         "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
                          "launches": up_n, "avg_launch_ms": (up_ms / up_n) if up_n else None,
                          "flops_per_launch": up_flops / up_n if up_n else None},
             "ms_per_sampling_step": ms_per_step / T,
@@ -279,6 +313,10 @@ def run_b200(args):
             "kernel_time_share": breakdown,
             "wall_s": wall,
         }
+        if world == 1 and not args.no_library_ref:
+            # Context for the fraction above, measured now on this GPU under the same power cap: cuBLASLt (torch.matmul) on the
+            # up-GEMM's shape, no epilogue, looped for ~2 s.  Library call used as a yardstick only -- never on the product path.
+            line["roofline"]["library_same_shape"] = library_sustained_tflops(torch, 2 * B * S, MLP, D)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             r = cpu_reference_sample(args.bits, args.cpu_batch, args.cpu_steps, T, threads)
@@ -371,6 +409,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-ref", action="store_true", help="skip the 2 s cuBLASLt same-shape yardstick loop")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e pass (profiling runs under ncu only)")
     args = ap.parse_args()
     if args.batch is None:

@@ -47,7 +47,7 @@ typedef struct mb_config {
     int codebook_splits;   /* mlm_model.codebook_splits (2) */
     int nclass;            /* 1000; index nclass is the dropped-label embedding (bert.py:371-372) */
     int seq_len;           /* (img_size / input_stride)^2 = 256 */
-    int use_prenorm;       /* must be 0: all shipped configs are post-norm */
+    int use_prenorm;       /* bert.py use_prenorm: 0 post-norm (every shipped config), 1 pre-norm + norm_after_transformer */
     int dec_hidden_channels;   /* vq_model.hidden_channels (128) */
     int dec_channel_mult[8];   /* vq_model.channel_mult */
     int dec_num_resolutions;   /* vq_model.num_resolutions (5) */

@@ -36,7 +36,8 @@ class LFQBert(EngineModel):
 
     def _arch(self):
         return dict(hidden_dim=self.hidden_dim, codebook_size=self.codebook_size, codebook_splits=self.splits,
-                    depth=self.depth, mlp_dim=self.mlp_dim, nclass=self.nclass, seq_len=self.seq_len)
+                    depth=self.depth, mlp_dim=self.mlp_dim, nclass=self.nclass, seq_len=self.seq_len,
+                    use_prenorm=bool(self.use_prenorm))
 
     def _expected_spec(self):
         return [(n, s) for n, s, _ in lfq_bert_spec(**self._arch())]

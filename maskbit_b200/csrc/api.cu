@@ -215,7 +215,7 @@ struct mb_handle {
     // generator
     int bits = 0, eff_bits = 0, V = 0, S = 0;  // S = seq_len + 1
     float *w_in_t = nullptr, *b_in = nullptr, *class_emb = nullptr, *pos = nullptr;
-    LNW ln_first, ln_head;
+    LNW ln_first, ln_head, ln_after, ln_ident;   // ln_after / ln_ident: pre-norm trunk only
     std::vector<Layer> layers;
     Linear head, pred;
     // generator workspace
@@ -285,7 +285,6 @@ extern "C" int mb_create(const mb_config* cfg, mb_handle** out) {
     if (!cfg || !out) return fail(MB_ERR_INVALID, "mb_create: null argument");
     if (cfg->hidden_dim != 1024) return fail(MB_ERR_INVALID, "hidden_dim %d unsupported (row kernels are built for 1024)", cfg->hidden_dim);
     if (cfg->heads <= 0 || cfg->hidden_dim / cfg->heads != 64) return fail(MB_ERR_INVALID, "head dim must be 64");
-    if (cfg->use_prenorm) return fail(MB_ERR_INVALID, "use_prenorm=True is not implemented (no shipped config uses it)");
     if (cfg->codebook_splits < 1 || cfg->token_bits % cfg->codebook_splits) return fail(MB_ERR_INVALID, "token_bits must divide by codebook_splits");
     const int V = 1 << (cfg->token_bits / cfg->codebook_splits);
     if (V < 32 || V > 512) return fail(MB_ERR_INVALID, "per-group vocabulary %d unsupported (32..512)", V);
@@ -460,16 +459,31 @@ static int finalize_generator(mb_handle* h) {
         MB_TRY(keep_ln(h, p + "1.norm", D, &h->layers[l].ln2));
     }
     MB_TRY(keep_ln(h, "last_layer.2", D, &h->ln_head));
+    const bool pre = c.use_prenorm != 0;
+    if (pre) {
+        // Pre-norm (bert.py:49-59,106-123,498-499): each block normalises its INPUT (its own .norm) and adds the un-normalised
+        // stream back, so the residual epilogue runs with the identity LayerNorm (gamma 1, beta 0, no statistics).
+        MB_TRY(keep_ln(h, "norm_after_transformer", D, &h->ln_after));
+        MB_TRY(dev_alloc(h, &h->ln_ident.g, (size_t)D));
+        MB_TRY(dev_alloc(h, &h->ln_ident.b, (size_t)D));
+        std::vector<float> ones(D, 1.0f);
+        CU_TRY(cudaMemcpy(h->ln_ident.g, ones.data(), D * sizeof(float), cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemset(h->ln_ident.b, 0, D * sizeof(float)));
+    }
     for (int l = 0; l < c.depth; ++l) {
         const std::string p = "transformer.layers." + std::to_string(l) + ".";
         Layer& L = h->layers[l];
-        const LNW& ln_in = l == 0 ? h->ln_first : h->layers[l - 1].ln2;     // x_l = LN_in(y): input of the attention block
+        // post-norm: x_l = LN_in(y) is the input of the attention block, LN1 its output norm (bert.py:137-139, 69-70)
+        const LNW& ln_in = pre ? L.ln1 : (l == 0 ? h->ln_first : h->layers[l - 1].ln2);
+        const LNW& ln_res_attn = pre ? h->ln_ident : ln_in;
+        const LNW& ln_mlp = pre ? L.ln2 : L.ln1;
+        const LNW& ln_res_mlp = pre ? h->ln_ident : L.ln1;
         MB_TRY(make_linear_lnin(h, p + "0.mha.in_proj_weight", p + "0.mha.in_proj_bias", 3 * D, D, ln_in, &L.qkv));
-        MB_TRY(make_linear_res(h, p + "0.mha.out_proj.weight", p + "0.mha.out_proj.bias", D, D, ln_in, &L.out));     // + x_l (bert.py:139)
-        MB_TRY(make_linear_lnin(h, p + "1.net.0.weight", p + "1.net.0.bias", c.mlp_dim, D, L.ln1, &L.up));
-        MB_TRY(make_linear_res(h, p + "1.net.2.weight", p + "1.net.2.bias", D, c.mlp_dim, L.ln1, &L.down));          // + LN1(y1) (bert.py:70)
+        MB_TRY(make_linear_res(h, p + "0.mha.out_proj.weight", p + "0.mha.out_proj.bias", D, D, ln_res_attn, &L.out));
+        MB_TRY(make_linear_lnin(h, p + "1.net.0.weight", p + "1.net.0.bias", c.mlp_dim, D, ln_mlp, &L.up));
+        MB_TRY(make_linear_res(h, p + "1.net.2.weight", p + "1.net.2.bias", D, c.mlp_dim, ln_res_mlp, &L.down));
     }
-    const LNW& ln_last = c.depth > 0 ? h->layers[c.depth - 1].ln2 : h->ln_first;
+    const LNW& ln_last = pre ? h->ln_after : (c.depth > 0 ? h->layers[c.depth - 1].ln2 : h->ln_first);
     MB_TRY(make_linear_lnin(h, "last_layer.0.weight", "last_layer.0.bias", D, D, ln_last, &h->head));
     MB_TRY(make_linear_lnin(h, "prediction_layer.weight", "prediction_layer.bias", c.codebook_splits * h->V, D, h->ln_head, &h->pred));
     // buffers of the reference module that carry no information for this path
@@ -782,18 +796,22 @@ static int forward_impl(mb_handle* h, const int64_t* tokens, int n_token_rows, c
         ProfScope prof(h, MB_PROF_EMBED, st);
         embed_kernel<D><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(tokens, n_token_rows, labels, n_label_rows, drop, n_seq, c.seq_len,
                                                                   c.codebook_splits, h->eff_bits, c.nclass, h->w_in_t, h->b_in,
-                                                                  h->class_emb, h->pos, h->yA, h->stA, LN_PARTIALS);
+                                                                  h->class_emb, h->pos, h->yA, h->stA, LN_PARTIALS,
+                                                                  c.use_prenorm ? h->ln_first.g : nullptr, c.use_prenorm ? h->ln_first.b : nullptr);
     }
     CU_TRY(cudaGetLastError()); h->launches++;
+    // pre-norm: the residual epilogues add the stream as stored (no statistics -> identity LayerNorm)
+    const float2* res_stA = c.use_prenorm ? nullptr : h->stA;
+    const float2* res_stB = c.use_prenorm ? nullptr : h->stB;
     for (int l = 0; l < c.depth; ++l) {
         const Layer& L = h->layers[l];
         // attention block (bert.py:137-139): yB = out_proj(MHA(LN(yA))) + LN(yA)
         MB_TRY(run_linear(h, MB_PROF_GEMM_QKV, h->tm_yA, L.qkv, M, EPI_LNIN_BF16, nullptr, h->stA, nullptr, h->qkv, &h->tmo_qkv, 3 * D, st));
         MB_TRY(run_attention(h, h->tm_qkv_big, h->tm_qkv_row, h->tmo_att, h->qkv, h->att, n_seq, h->S, D, c.heads, h->num_sms, st));
-        MB_TRY(run_linear(h, MB_PROF_GEMM_OUT, h->tm_att, L.out, M, EPI_RES_LN_BF16_STATS, h->yA, h->stA, h->stB, h->yB, &h->tmo_yB, D, st));
+        MB_TRY(run_linear(h, MB_PROF_GEMM_OUT, h->tm_att, L.out, M, EPI_RES_LN_BF16_STATS, h->yA, res_stA, h->stB, h->yB, &h->tmo_yB, D, st));
         // feed-forward block (bert.py:69-70): yA = W2 gelu(W1 LN1(yB) + b1) + b2 + LN1(yB)
         MB_TRY(run_linear(h, MB_PROF_GEMM_UP, h->tm_yB, L.up, M, EPI_LNIN_GELU_BF16, nullptr, h->stB, nullptr, h->hmid, &h->tmo_hmid, c.mlp_dim, st));
-        MB_TRY(run_linear(h, MB_PROF_GEMM_DOWN, h->tm_hmid, L.down, M, EPI_RES_LN_BF16_STATS, h->yB, h->stB, h->stA, h->yA, &h->tmo_yA, D, st));
+        MB_TRY(run_linear(h, MB_PROF_GEMM_DOWN, h->tm_hmid, L.down, M, EPI_RES_LN_BF16_STATS, h->yB, res_stB, h->stA, h->yA, &h->tmo_yA, D, st));
     }
     // head (bert.py:500-503): LN(gelu(W LN2(yA) + b)) -> prediction layer, class-token row dropped
     MB_TRY(run_linear(h, MB_PROF_GEMM_HEAD, h->tm_yA, h->head, M, EPI_LNIN_GELU_BF16_STATS, nullptr, h->stA, h->stB, h->yB, &h->tmo_yB, D, st));

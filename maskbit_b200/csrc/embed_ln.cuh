@@ -22,12 +22,15 @@ __device__ __forceinline__ float warp_sum(float v) {
 //          (drop == nullptr: every label dropped -- the reference's drop_label_mask=None quirk, bert.py:484)
 // w_in_t   fp32 [bits, D] = input_proj.weight transposed;  pos fp32 [seq_len+1, D];  class_emb fp32 [nclass+1, D]
 // y        bf16 [rows, D] pre-LayerNorm sum;  stats float2 [rows][n_partials]: slot 0 = (sum, sumsq) of the stored row, rest 0
+// ln_g/ln_b  nullptr for the post-norm trunk.  Pre-norm trunk (use_prenorm, bert.py:496 with :106-123): the residual stream carries
+//          first_layer's LayerNorm OUTPUT, so it is applied here (fp32 statistics of the fp32 row, eps 1e-12) before the store.
 template <int D>
 __global__ void __launch_bounds__(256)
 embed_kernel(const int64_t* __restrict__ tokens, int n_token_rows, const int64_t* __restrict__ labels, int n_label_rows,
              const uint8_t* __restrict__ drop, int n_seq, int seq_len, int splits, int eff_bits, int nclass,
              const float* __restrict__ w_in_t, const float* __restrict__ b_in, const float* __restrict__ class_emb,
-             const float* __restrict__ pos, __nv_bfloat16* __restrict__ y, float2* __restrict__ stats, int n_partials) {
+             const float* __restrict__ pos, __nv_bfloat16* __restrict__ y, float2* __restrict__ stats, int n_partials,
+             const float* __restrict__ ln_g = nullptr, const float* __restrict__ ln_b = nullptr) {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long rows = (long long)n_seq * (seq_len + 1);
@@ -66,13 +69,36 @@ embed_kernel(const int64_t* __restrict__ tokens, int n_token_rows, const int64_t
             x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
         }
     }
+#pragma unroll
+    for (int j = 0; j < D / 128; ++j) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(prow + 4 * (lane + 32 * j)));
+        x[4 * j] += v.x; x[4 * j + 1] += v.y; x[4 * j + 2] += v.z; x[4 * j + 3] += v.w;
+    }
+    if (ln_g != nullptr) {   // two-pass LayerNorm in registers
+        float s1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < D / 32; ++i) s1 += x[i];
+        const float mean = warp_sum(s1) * (1.0f / D);
+        float s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < D / 32; ++i) { const float d = x[i] - mean; s2 = fmaf(d, d, s2); }
+        const float rstd = rsqrtf(warp_sum(s2) * (1.0f / D) + 1e-12f);
+#pragma unroll
+        for (int j = 0; j < D / 128; ++j) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(ln_g + 4 * (lane + 32 * j)));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(ln_b + 4 * (lane + 32 * j)));
+            x[4 * j] = fmaf((x[4 * j] - mean) * rstd, g.x, b.x);
+            x[4 * j + 1] = fmaf((x[4 * j + 1] - mean) * rstd, g.y, b.y);
+            x[4 * j + 2] = fmaf((x[4 * j + 2] - mean) * rstd, g.z, b.z);
+            x[4 * j + 3] = fmaf((x[4 * j + 3] - mean) * rstd, g.w, b.w);
+        }
+    }
     float sum = 0.f, sq = 0.f;
     __nv_bfloat16* orow = y + (size_t)row * D;
 #pragma unroll
     for (int j = 0; j < D / 128; ++j) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(prow + 4 * (lane + 32 * j)));
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(x[4 * j] + v.x, x[4 * j + 1] + v.y);
-        __nv_bfloat162 h1 = __floats2bfloat162_rn(x[4 * j + 2] + v.z, x[4 * j + 3] + v.w);
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(x[4 * j], x[4 * j + 1]);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(x[4 * j + 2], x[4 * j + 3]);
         const float a = __low2float(h0), b = __high2float(h0), c = __low2float(h1), d = __high2float(h1);
         sum += (a + b) + (c + d);                                   // statistics of the values as stored
         sq = fmaf(a, a, fmaf(b, b, fmaf(c, c, fmaf(d, d, sq))));

@@ -236,7 +236,8 @@ __device__ __forceinline__ EpiRow epi_prepare(const GemmParams& p, int row) {
     }
     // LayerNorm row statistics: of the A row for LN-in modes, of the residual-stream row for the residual mode
     r.rs = 1.f; r.nmr = 0.f;                // rstd, -mean * rstd
-    if ((kLnIn || EPI == EPI_RES_LN_BF16_STATS) && r.row_ok) {
+    // (residual mode with stats_in == nullptr: the residual is added as stored, rs = 1, nmr = 0 -- the pre-norm trunk)
+    if ((kLnIn || EPI == EPI_RES_LN_BF16_STATS) && r.row_ok && p.stats_in != nullptr) {
         float mean, rstd;
         ln_row_stats(p.stats_in + (size_t)row * LN_PARTIALS, p.inv_d, p.eps, mean, rstd);
         r.rs = rstd; r.nmr = -mean * rstd;

@@ -49,7 +49,7 @@ def _t(name, shape, scale, seed, mean=0.0):
 
 
 def lfq_bert_spec(hidden_dim=1024, codebook_size=4096, codebook_splits=2, depth=24, mlp_dim=4096, nclass=1000,
-                  seq_len=256):
+                  seq_len=256, use_prenorm=False):
     """(name, shape, kind) for every LFQBert tensor, in state_dict order."""
     bits = int(math.log2(codebook_size))
     eff = bits // codebook_splits
@@ -66,6 +66,8 @@ def lfq_bert_spec(hidden_dim=1024, codebook_size=4096, codebook_splits=2, depth=
                  (p + "1.net.0.weight", (mlp_dim, D), "w"), (p + "1.net.0.bias", (mlp_dim,), "b"),
                  (p + "1.net.2.weight", (D, mlp_dim), "w"), (p + "1.net.2.bias", (D,), "b"),
                  (p + "1.norm.weight", (D,), "g"), (p + "1.norm.bias", (D,), "b")]
+    if use_prenorm:   # bert.py:407-408
+        spec += [("norm_after_transformer.weight", (D,), "g"), ("norm_after_transformer.bias", (D,), "b")]
     spec += [("last_layer.0.weight", (D, D), "w"), ("last_layer.0.bias", (D,), "b"),
              ("last_layer.2.weight", (D,), "g"), ("last_layer.2.bias", (D,), "b"),
              ("prediction_layer.weight", (codebook_splits * 2 ** eff, D), "w"),

@@ -95,11 +95,13 @@ def mha(x, w_in, b_in, w_out, b_out, heads):
 
 def lfq_bert_forward(sd, img_tokens, class_labels, drop_label_mask, *, heads=16, splits=2, nclass=1000,
                      return_hidden=False):
-    """LFQBert.forward, post-norm (bert.py:456-508).  Returns fp32 logits [N, seq_len, splits, V].
+    """LFQBert.forward (bert.py:456-508), post-norm, or pre-norm when the checkpoint carries ``norm_after_transformer``
+    (use_prenorm=True: bert.py:49-59,106-123,407-408,498-499).  Returns fp32 logits [N, seq_len, splits, V].
 
     Does not mutate class_labels (the reference mutates a view in place, bert.py:484; harmless in sample()).
     drop_label_mask=None reproduces the reference quirk ``cls_token[None] = 1000`` (drops every label).
     """
+    prenorm = "norm_after_transformer.weight" in sd
     bits = sd["input_proj.weight"].shape[1]
     n, seq_len, _ = img_tokens.shape
     x_bits = preprocess_tokens(img_tokens, bits, splits)
@@ -116,13 +118,24 @@ def lfq_bert_forward(sd, img_tokens, class_labels, drop_label_mask, *, heads=16,
     depth = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("transformer.layers."))
     for l in range(depth):
         p = f"transformer.layers.{l}."
-        a = mha(x, sd[p + "0.mha.in_proj_weight"], sd[p + "0.mha.in_proj_bias"],
-                sd[p + "0.mha.out_proj.weight"], sd[p + "0.mha.out_proj.bias"], heads)
-        x = layer_norm(a + x, sd[p + "0.norm.weight"], sd[p + "0.norm.bias"])            # bert.py:137-139
-        h = gelu_erf(x @ sd[p + "1.net.0.weight"].t() + sd[p + "1.net.0.bias"])
-        h = h @ sd[p + "1.net.2.weight"].t() + sd[p + "1.net.2.bias"]
-        x = layer_norm(h + x, sd[p + "1.norm.weight"], sd[p + "1.norm.bias"])            # bert.py:69-70
+
+        def attn(t):
+            return mha(t, sd[p + "0.mha.in_proj_weight"], sd[p + "0.mha.in_proj_bias"],
+                       sd[p + "0.mha.out_proj.weight"], sd[p + "0.mha.out_proj.bias"], heads)
+
+        def mlp(t):
+            h = gelu_erf(t @ sd[p + "1.net.0.weight"].t() + sd[p + "1.net.0.bias"])
+            return h @ sd[p + "1.net.2.weight"].t() + sd[p + "1.net.2.bias"]
+
+        if prenorm:
+            x = attn(layer_norm(x, sd[p + "0.norm.weight"], sd[p + "0.norm.bias"])) + x        # bert.py:118-121
+            x = mlp(layer_norm(x, sd[p + "1.norm.weight"], sd[p + "1.norm.bias"])) + x         # bert.py:57-59
+        else:
+            x = layer_norm(attn(x) + x, sd[p + "0.norm.weight"], sd[p + "0.norm.bias"])        # bert.py:137-139
+            x = layer_norm(mlp(x) + x, sd[p + "1.norm.weight"], sd[p + "1.norm.bias"])         # bert.py:69-70
         hidden.append(x)
+    if prenorm:
+        x = layer_norm(x, sd["norm_after_transformer.weight"], sd["norm_after_transformer.bias"])   # bert.py:498-499
     y = gelu_erf(x @ sd["last_layer.0.weight"].t() + sd["last_layer.0.bias"])
     y = layer_norm(y, sd["last_layer.2.weight"], sd["last_layer.2.bias"])                  # bert.py:500
     logits = y @ sd["prediction_layer.weight"].t() + sd["prediction_layer.bias"]

@@ -44,5 +44,31 @@ def full(path):
             print(f"  {hdr[i]:85s} {r[i][:100]} {units[i]}")
 
 
+def traffic(path):
+    """dram bytes (read + write) per launch for each trunk kernel class of a full capture -> JSON on stdout
+    (committed as profiles/ncu_traffic.json and read by bench.py's roofline.traffic)."""
+    import json
+    raw = subprocess.check_output(["ncu", "-i", path, "--page", "raw", "--csv"], text=True)
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    kinds = {"gemm2_bf16_tcgen05_kernel<5>": "gemm_qkv", "gemm2_bf16_tcgen05_kernel<6>": "gemm_up", "attention_tc_kernel": "attention"}
+    acc = collections.defaultdict(list)
+    seen7 = 0
+    for r in rows[2:]:
+        name = re.sub(r"\(int\)", "", r[ki])
+        b = float(r[ri].replace(",", "")) * scale[units[ri]] + float(r[wi].replace(",", "")) * scale[units[wi]]
+        kind = next((v for k, v in kinds.items() if k in name), None)
+        if kind is None and "gemm2_bf16_tcgen05_kernel<7>" in name:   # out-projection and MLP-down alternate within a layer
+            kind = "gemm_out" if seen7 % 2 == 0 else "gemm_down"
+            seen7 += 1
+        if kind:
+            acc[kind].append(b)
+    out = {k: {"dram_bytes_per_launch": sum(v) / len(v), "launches_captured": len(v)} for k, v in acc.items()}
+    out["_source"] = f"ncu --set full --clock-control none capture {path} (profiles/run_profile.sh), B=256 -> 512 sequences per forward"
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])

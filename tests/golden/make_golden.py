@@ -11,6 +11,8 @@ Fixtures written (all small enough to commit):
   select_12bit.npz    sample() B=2, 4 steps: per-step generator logits (forward hook), replayed RNG draws
                       (q ~ Exp(1), g ~ Gumbel) and the reference's per-step predicted tokens
   sample_12bit.npz    BASELINE config #1: sample() B=4, 8 steps, CFG cosine: per-step tokens + pixels
+  forward_prenorm_12bit.npz  LFQBert(use_prenorm=True, depth=2).forward, 2 sequences (no shipped config uses pre-norm; the
+                      branch is bert.py:49-59,106-123,498-499)
   decode_12bit.npz    ConvVQModel.decode_tokens on random tokens, B=2
   encode_12bit.npz    ConvVQModel.forward (encode -> LFQ -> decode) on seeded images, B=2: latents z, indices, reconstruction
 """
@@ -72,6 +74,15 @@ def golden_forward(gen, bits, n, path):
     np.savez_compressed(path, tokens=tok.numpy().astype(np.int16), labels=labels.numpy(), drop=drop.numpy(),
                         logits=logits.numpy())
     print(path, logits.shape, float(logits.abs().max()))
+
+
+def golden_forward_prenorm(path):
+    """Pre-norm branch on a 2-layer generator of the shipped width (hidden 1024, 16 heads, MLP 4096, 12-bit)."""
+    gen = LFQBert(img_size=256, hidden_dim=1024, codebook_size=4096, codebook_splits=2, depth=2, heads=16, mlp_dim=4096,
+                  dropout=0.1, use_prenorm=True, input_stride=16)
+    gen.load_state_dict(synthetic_lfq_bert_state_dict(seed=3, codebook_size=4096, depth=2, use_prenorm=True), strict=True)
+    gen.eval().requires_grad_(False)
+    golden_forward(gen, 12, 2, path)
 
 
 def golden_sample(kw, vq, gen, b, steps, path, with_logits):
@@ -137,6 +148,7 @@ def main():
     torch.set_num_threads(os.cpu_count())
     cfg, kw, vq, gen = build_reference(12)
     golden_forward(gen, 12, 4, os.path.join(HERE, "forward_12bit.npz"))
+    golden_forward_prenorm(os.path.join(HERE, "forward_prenorm_12bit.npz"))
     golden_decode(vq, 12, os.path.join(HERE, "decode_12bit.npz"))
     golden_encode(vq, os.path.join(HERE, "encode_12bit.npz"))
     golden_sample(kw, vq, gen, 2, 4, os.path.join(HERE, "select_12bit.npz"), with_logits=True)

@@ -107,6 +107,27 @@ def test_forward_other_shipped_widths_vs_oracle(bits):
     assert d.max().item() <= LOGIT_MAX_ABS and d.mean().item() <= LOGIT_MEAN_ABS
 
 
+def test_forward_prenorm_matches_reference_golden(golden_dir):
+    """use_prenorm=True (bert.py:49-59,106-123,498-499; no shipped config uses it): 2-layer generator of the shipped width
+    against the reference's own logits on the same synthetic checkpoint, and the strict loader knows the extra norm."""
+    from maskbit_b200.weights import synthetic_lfq_bert_state_dict
+    d = np.load(os.path.join(golden_dir, "forward_prenorm_12bit.npz"))
+    gen = LFQBert(img_size=256, hidden_dim=1024, codebook_size=4096, codebook_splits=2, depth=2, heads=16, mlp_dim=4096,
+                  dropout=0.1, use_prenorm=True, input_stride=16)
+    sd = synthetic_lfq_bert_state_dict(seed=3, codebook_size=4096, depth=2, use_prenorm=True)
+    assert "norm_after_transformer.weight" in sd
+    gen.load_state_dict(sd, strict=True)
+    gen = gen.to("cuda")
+    logits = gen(torch.from_numpy(d["tokens"].astype(np.int64)).cuda(), torch.from_numpy(d["labels"]).cuda(),
+                 torch.from_numpy(d["drop"]).cuda()).cpu()
+    diff = (logits - torch.from_numpy(d["logits"])).abs()
+    assert diff.max().item() <= LOGIT_MAX_ABS and diff.mean().item() <= LOGIT_MEAN_ABS, (diff.max().item(), diff.mean().item())
+    post = LFQBert(img_size=256, hidden_dim=1024, codebook_size=4096, codebook_splits=2, depth=2, heads=16, mlp_dim=4096,
+                   dropout=0.1, use_prenorm=False, input_stride=16)
+    with pytest.raises(Exception):
+        post.load_state_dict(sd, strict=True)          # the post-norm model has no norm_after_transformer
+
+
 def test_forward_drop_none_and_batch_invariance(golden_dir):
     """drop_label_mask=None drops every label (the reference quirk `cls_token[None] = 1000`, bert.py:482-484), and a
     sequence's logits do not depend on what else is in the batch (bit-exact: tiles never mix sequences' rows)."""
@@ -398,6 +419,36 @@ def test_sample_matches_stepwise_composition():
         if gs != 0.0:
             img2, trace2 = sample(gen, tokenizer, num_samples=B, labels=labels, noise=(q, gum), skip_zero_scale_uncond=True, **kws)
             assert all(torch.equal(a, b) for a, b in zip(trace, trace2)) and torch.equal(img, img2)
+
+
+@pytest.mark.parametrize("strategy,annealing,sampling_annealing,temperature",
+                         [("linear", "none", False, 1.0), ("root", "linear", False, 0.8), ("square", "cosine", True, 1.0),
+                          ("cosine", "none", True, 1.3), ("arccos", "linear", True, 1.0)])
+def test_sample_modes_vs_c_oracle(strategy, annealing, sampling_annealing, temperature):
+    """Every schedule / guidance-annealing / temperature-annealing mode of the reference (masking.py:51-62,
+    sampling.py:88-97,103): the device-resident loop of mb_sample, step by step, equals the plain-C select oracle applied
+    to the CUDA forward's logits with the same injected noise and the host schedule tables (bit-exact tokens)."""
+    _, kw, tokenizer, gen = models(12)
+    B, steps = 2, 4
+    gcpu = torch.Generator().manual_seed(23)
+    labels = torch.randint(0, 1000, (B,), generator=gcpu)
+    q = torch.empty((steps, B * 512, 64)).exponential_(1, generator=gcpu)
+    gum = -torch.log(-torch.log(torch.rand((steps, B, 256, 2), generator=gcpu).clamp_min(1e-20)))
+    kws = dict(kw, num_steps=steps, mask_schedule_strategy=strategy, guidance_annealing=annealing,
+               use_sampling_annealing=sampling_annealing, softmax_temperature=temperature)
+    _, trace = sample(gen, tokenizer, num_samples=B, labels=labels, noise=(q, gum), **kws)
+    scale, temp, omp, mask_len = step_tables(steps, 512, softmax_temperature=temperature, mask_schedule_strategy=strategy,
+                                             guidance_scale=kw["guidance_scale"], guidance_annealing=annealing,
+                                             scale_pow=kw["scale_pow"], use_sampling_annealing=sampling_annealing)
+    masked = torch.full((B, 256, 2), kw["mask_token"], dtype=torch.int64)
+    drop = torch.cat([torch.zeros(B, dtype=torch.bool), torch.ones(B, dtype=torch.bool)]).cuda()
+    lab2 = torch.cat([labels, labels]).cuda()
+    for i in range(steps):
+        logits = gen(torch.cat([masked, masked]).cuda(), lab2, drop).cpu()
+        pred, nxt, _ = SO.select_step(logits[:B].numpy(), logits[B:].numpy(), scale[i], temp[i], q[i].numpy(), gum[i].numpy(),
+                                      kw["randomize_temperature"], omp[i], mask_len[i], masked.numpy(), kw["mask_token"])
+        assert np.array_equal(trace[i].cpu().numpy(), pred), f"{strategy}/{annealing} step {i}"
+        masked = torch.from_numpy(np.asarray(nxt)).to(torch.int64)
 
 
 def test_sample_device_noise_full_size_properties():
