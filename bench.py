@@ -209,6 +209,9 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL prints its version banner (NCCL_DEBUG=VERSION on the GPU boxes) to stdout by default: keep stdout to the one
+        # JSON line the driver parses
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = load_config(f"maskbit_generator_{args.bits}bit")

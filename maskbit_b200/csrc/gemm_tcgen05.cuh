@@ -31,6 +31,9 @@
 #ifndef GEMM_TIMING_NO_STATS
 #define GEMM_TIMING_NO_STATS 0   // timing experiments only: skip the row-statistics stores of the STATS epilogues
 #endif
+#ifndef GEMM_TIMING_NO_RES_LOAD
+#define GEMM_TIMING_NO_RES_LOAD 0   // timing experiments only: residual epilogue runs on a zero slab (no residual loads)
+#endif
 #ifndef GEMM_TIMING_NO_MMA
 #define GEMM_TIMING_NO_MMA 0     // timing experiments only (CTA-pair kernel): issue no MMAs, keep loads + barriers + epilogue
 #endif
@@ -217,6 +220,7 @@ __device__ __forceinline__ void epi_load_residual(const GemmParams& p, const Epi
     const __nv_bfloat16* rp = p.residual + (size_t)(er.row_ok ? er.row : 0) * p.ldr + col0;
 #pragma unroll
     for (int i = 0; i < COLS / 16; ++i)
+        if (GEMM_TIMING_NO_RES_LOAD) { s.v[2 * i] = make_uint4(0, 0, 0, 0); s.v[2 * i + 1] = make_uint4(0, 0, 0, 0); } else
         asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                      : "=r"(s.v[2 * i].x), "=r"(s.v[2 * i].y), "=r"(s.v[2 * i].z), "=r"(s.v[2 * i].w), "=r"(s.v[2 * i + 1].x),
                        "=r"(s.v[2 * i + 1].y), "=r"(s.v[2 * i + 1].z), "=r"(s.v[2 * i + 1].w)
