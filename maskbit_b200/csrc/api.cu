@@ -227,6 +227,7 @@ struct mb_handle {
     CUtensorMap tmo_yA, tmo_yB, tmo_qkv, tmo_hmid, tmo_att;   // output maps (box 64 x 32) of the same buffers
     // sampler workspace
     int cap_sample_B = 0;
+    int drop_layout_B = 0;   // batch the drop flags in drop_ws are currently laid out for ([0]*B then [1]*B)
     int64_t *tok_a = nullptr, *tok_b = nullptr, *pred_buf = nullptr, *combined = nullptr;
     float* logits_ws = nullptr; uint8_t* drop_ws = nullptr;
     // decoder
@@ -315,7 +316,7 @@ static void free_ws(mb_handle* h) {
 static void free_sample_ws(mb_handle* h) {
     void* ps[] = {h->tok_a, h->tok_b, h->pred_buf, h->combined, h->logits_ws, h->drop_ws};
     for (void* p : ps) if (p) cudaFree(p);
-    h->tok_a = h->tok_b = h->pred_buf = h->combined = nullptr; h->logits_ws = nullptr; h->drop_ws = nullptr; h->cap_sample_B = 0;
+    h->tok_a = h->tok_b = h->pred_buf = h->combined = nullptr; h->logits_ws = nullptr; h->drop_ws = nullptr; h->cap_sample_B = 0; h->drop_layout_B = 0;
 }
 static void free_dec_ws(mb_handle* h) {
     void* ps[] = {h->dx, h->dt1, h->dt2, h->gn_scale, h->gn_shift, h->gn_partial, h->act_hi, h->act_lo};
@@ -1085,6 +1086,7 @@ static int ensure_sample_ws(mb_handle* h, int B) {
     CU_TRY(cudaMemset(h->drop_ws, 0, B));
     CU_TRY(cudaMemset(h->drop_ws + B, 1, B));
     h->cap_sample_B = B;
+    h->drop_layout_B = B;
     return 0;
 }
 
@@ -1095,9 +1097,10 @@ extern "C" int mb_sample(mb_handle* h, const mb_sample_args* a, mb_stream stream
     const mb_config& c = h->cfg;
     const int B = a->B;
     MB_TRY(ensure_sample_ws(h, B));
-    if (B != h->cap_sample_B) {  // drop flags are laid out for the capacity batch; rebuild for this B
-        CU_TRY(cudaMemsetAsync(h->drop_ws, 0, B, st));
+    if (B != h->drop_layout_B) {  // the conditional / unconditional drop flags sit at [0, B) / [B, 2B): rebuild when B changes
+        CU_TRY(cudaMemsetAsync(h->drop_ws, 0, B, st));   // (comparing against the capacity here left a smaller call's layout behind)
         CU_TRY(cudaMemsetAsync(h->drop_ws + B, 1, B, st));
+        h->drop_layout_B = B;
     }
     const size_t slots = (size_t)c.seq_len * c.codebook_splits;
     const int64_t mask_token = (int64_t)1 << h->eff_bits;

@@ -31,6 +31,9 @@
 #ifndef GEMM_TIMING_NO_STATS
 #define GEMM_TIMING_NO_STATS 0   // timing experiments only: skip the row-statistics stores of the STATS epilogues
 #endif
+#ifndef GEMM_GELU_MODE
+#define GEMM_GELU_MODE 2         // 0: MUFU-erf form and polynomial form alternating pair by pair | 1: polynomial only | 2: MUFU form only
+#endif
 #ifndef GEMM_TIMING_NO_RES_LOAD
 #define GEMM_TIMING_NO_RES_LOAD 0   // timing experiments only: residual epilogue runs on a zero slab (no residual loads)
 #endif
@@ -158,8 +161,11 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
 
 // The same two GELUs without the MUFU pipe: Phi(x) - 0.5 = x * Q(x^2), Q a degree-9 least-squares polynomial on x^2 <= 4.5^2
 // (Phi saturated to 0 / 1 beyond: Phi(4.5) = 1 - 3.4e-6); |gelu error| <= 5e-5 at |x| ~ 4.5 and ~1e-5 elsewhere, far below the bf16
-// rounding of the stored value.  The GELU epilogue alternates the two forms pair by pair: with erf on the MUFU form alone
-// the special-function pipe (16 ops / clk / SM, two per element) is as busy as the tensor pipe over a 128 x 256 x 1024 tile.
+// rounding of the stored value.  GEMM_GELU_MODE picks the mix.  When the epilogue was the up-projection's critical path the two
+// forms alternated pair by pair (MUFU form alone: the special-function pipe, 16 ops / clk / SM and two per element, was as busy
+// as the tensor pipe over a 128 x 256 x 1024 tile).  With the epilogue overlapped, the job is energy-bound and the MUFU form
+// alone measures 1 % less energy per launch than either the mix or the polynomial alone (tools/kpower.py), and is the more
+// accurate of the two: it is the default.
 __device__ __forceinline__ void gelu_poly2(float& x0, float& x1) {
     // t = min(x^2, 4.5^2): beyond the fitted range x Q(t) is linear in x with slope Q(4.5^2) = (0.5 - 3.4e-6) / 4.5, so
     // 0.5 + x Q(t) leaves [0, 1] there and the saturating FMA returns Phi = 0 / 1 -- no clamp of x itself.
@@ -303,7 +309,11 @@ __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, u
         }
         if (kGelu && !GEMM_TIMING_NO_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) { gelu_erf2(f[j], f[j + 1]); gelu_poly2(f[j + 2], f[j + 3]); }
+            for (int j = 0; j < 32; j += 4) {
+                if (GEMM_GELU_MODE == 1) { gelu_poly2(f[j], f[j + 1]); gelu_poly2(f[j + 2], f[j + 3]); }
+                else if (GEMM_GELU_MODE == 2) { gelu_erf2(f[j], f[j + 1]); gelu_erf2(f[j + 2], f[j + 3]); }
+                else { gelu_erf2(f[j], f[j + 1]); gelu_poly2(f[j + 2], f[j + 3]); }
+            }
         }
         if (EPI == EPI_BIAS_RES_F32 || EPI == EPI_RES_LN_BF16_STATS) {
             if (row_ok) {

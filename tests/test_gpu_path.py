@@ -471,6 +471,34 @@ def test_sample_device_noise_full_size_properties():
     assert not torch.equal(trace_c[0], trace_d[0])
 
 
+def test_eval_driver_loop_matches_manual_batches():
+    """maskbit_b200.eval_driver.generate_samples (the loop of eval_maskbit.py:107-135) == calling sample() + the uint8
+    post-processing batch by batch with the same labels and seeds, including a ragged last batch."""
+    from maskbit_b200.eval_driver import generate_samples, label_schedule
+    from maskbit_b200.sharding import rank_seed
+    cfg, kw, tokenizer, gen = models(12)
+    imgs, labels = generate_samples(cfg, total_samples=5, batchsize=2, models=(tokenizer, gen), label_seed=3, noise_seed=11)
+    assert imgs.shape == (5, 256, 256, 3) and imgs.dtype == np.uint8 and torch.equal(labels, label_schedule(5, label_seed=3))
+    kws = dict(kw, softmax_temperature=1.0)
+    for i, (lo, hi) in enumerate([(0, 2), (2, 4), (4, 5)]):
+        ref, _ = sample(gen, tokenizer, num_samples=hi - lo, labels=labels[lo:hi], noise="device", seed=rank_seed(11 + i, 0),
+                        return_trace=False, **kws)
+        ref_u8 = (torch.clamp(ref, 0.0, 1.0) * 255.0).permute(0, 2, 3, 1).to("cpu", dtype=torch.uint8).numpy()   # eval_maskbit.py:134-135
+        assert np.array_equal(imgs[lo:hi], ref_u8)
+
+
+def test_sample_batch_size_changes_between_calls():
+    """One handle, batch sizes 3 -> 1 -> 3: the CFG drop-flag layout must follow the batch of the CALL (a smaller call used to
+    leave its layout behind for the next capacity-sized one)."""
+    _, kw, tokenizer, gen = models(12)
+    kws = dict(kw, num_steps=6)
+    labels = torch.tensor([3, 500, 999])
+    _, first = sample(gen, tokenizer, num_samples=3, labels=labels, noise="device", seed=5, **kws)
+    sample(gen, tokenizer, num_samples=1, labels=labels[:1], noise="device", seed=5, **kws)
+    _, again = sample(gen, tokenizer, num_samples=3, labels=labels, noise="device", seed=5, **kws)
+    assert all(torch.equal(a, b) for a, b in zip(first, again))
+
+
 def test_sample_argument_errors():
     _, kw, tokenizer, gen = models(12)
     with pytest.raises(ValueError):

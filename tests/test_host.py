@@ -144,3 +144,12 @@ def test_state_dict_layout_and_save_load_roundtrip(tmp_path):
     with pytest.raises(RuntimeError, match="Missing key"):
         tok2.load_state_dict(bad)
     assert maskbit_b200.split_factorized_tokens(torch.tensor([[37]]), 4096, 2).tolist() == [[[37, 0]]]
+
+
+def test_eval_driver_label_schedule():
+    """eval_maskbit.py:107-112: randperm(1000) repeated, cut into consecutive batches -- every block of 1000 holds each class once."""
+    from maskbit_b200.eval_driver import label_schedule
+    lab = label_schedule(2500, label_seed=5)
+    assert lab.dtype == torch.int64 and lab.shape == (2500,)
+    assert sorted(lab[:1000].tolist()) == list(range(1000)) and torch.equal(lab[:1000], lab[1000:2000]) and torch.equal(lab[:500], lab[2000:])
+    assert torch.equal(lab, label_schedule(2500, label_seed=5)) and not torch.equal(lab, label_schedule(2500, label_seed=6))
