@@ -246,6 +246,8 @@ struct mb_handle {
     int dec_cap = 0;
     float *dx = nullptr, *dt1 = nullptr, *dt2 = nullptr, *gn_scale = nullptr, *gn_shift = nullptr;
     double2* gn_partial = nullptr;
+    float2* gn_box = nullptr;            // per-box GroupNorm partials written by the conv epilogue (ConvTcParams::gn_part)
+    const float* gn_box_src = nullptr;   // the activation those partials describe (nullptr: none valid)
     __nv_bfloat16 *act_hi = nullptr, *act_lo = nullptr;   // zero-bordered bf16 hi / lo split of the current conv input
     std::map<std::vector<uint64_t>, CUtensorMap> tmap_cache;   // activation / output maps keyed by (pointer, shape, box)
     // per-kernel-class CUDA-event timing (mb_profile_*): pairs of events recorded around launches on the launch stream
@@ -319,9 +321,9 @@ static void free_sample_ws(mb_handle* h) {
     h->tok_a = h->tok_b = h->pred_buf = h->combined = nullptr; h->logits_ws = nullptr; h->drop_ws = nullptr; h->cap_sample_B = 0; h->drop_layout_B = 0;
 }
 static void free_dec_ws(mb_handle* h) {
-    void* ps[] = {h->dx, h->dt1, h->dt2, h->gn_scale, h->gn_shift, h->gn_partial, h->act_hi, h->act_lo};
+    void* ps[] = {h->dx, h->dt1, h->dt2, h->gn_scale, h->gn_shift, h->gn_partial, h->act_hi, h->act_lo, h->gn_box};
     for (void* p : ps) if (p) cudaFree(p);
-    h->dx = h->dt1 = h->dt2 = h->gn_scale = h->gn_shift = nullptr; h->gn_partial = nullptr; h->act_hi = h->act_lo = nullptr;
+    h->dx = h->dt1 = h->dt2 = h->gn_scale = h->gn_shift = nullptr; h->gn_partial = nullptr; h->act_hi = h->act_lo = nullptr; h->gn_box = nullptr; h->gn_box_src = nullptr;
     h->tmap_cache.clear(); h->dec_cap = 0;
 }
 
@@ -886,6 +888,10 @@ static int ensure_dec_ws(mb_handle* h, int nb) {
     MB_TRY(dev_alloc(h, &h->gn_scale, (size_t)nb * 1024, false));
     MB_TRY(dev_alloc(h, &h->gn_shift, (size_t)nb * 1024, false));
     MB_TRY(dev_alloc(h, &h->gn_partial, (size_t)nb * 64 * 32, false));
+    {   // one float2 per (32-pixel box, group) of the largest conv output
+        const int Rimg = P << (h->cfg.dec_num_resolutions - 1);
+        MB_TRY(dev_alloc(h, &h->gn_box, (size_t)nb * Rimg * Rimg, false));      // (R^2 / 32 boxes) * 32 groups
+    }
     // padded split inputs: the largest (R+2)^2 * C over the conv inputs (an upsample conv reads its input at the output size)
     size_t max_pad = 0;
     {
@@ -911,9 +917,15 @@ static int ensure_dec_ws(mb_handle* h, int nb) {
 
 static int run_gn(mb_handle* h, const float* x, const GNW& g, int nb, int R, cudaStream_t st) {
     const int HW = R * R;
-    int chunks = HW / 1024; if (chunks < 1) chunks = 1; if (chunks > 64) chunks = 64;
     ProfScope prof(h, MB_PROF_DEC_GN, st);
-    gn_partial_kernel<<<dim3(chunks, nb), 256, 0, st>>>(x, h->gn_partial, HW, g.C, chunks);
+    int chunks = 1;
+    if (h->gn_box_src == x) {
+        // x was written by conv_tcgen05_kernel, whose epilogue left per-box partial sums: no pass over the activation
+        gn_reduce_kernel<<<nb, 256, 0, st>>>(h->gn_box, h->gn_partial, HW / 32);
+    } else {
+        chunks = HW / 1024; if (chunks < 1) chunks = 1; if (chunks > 64) chunks = 64;
+        gn_partial_kernel<<<dim3(chunks, nb), 256, 0, st>>>(x, h->gn_partial, HW, g.C, chunks);
+    }
     CU_TRY(cudaGetLastError()); h->launches++;
     gn_finalize_kernel<<<nb, 256, 0, st>>>(h->gn_partial, g.g, g.b, h->gn_scale, h->gn_shift, HW, g.C, chunks, 1e-6f);
     CU_TRY(cudaGetLastError()); h->launches++;
@@ -949,6 +961,12 @@ static int run_conv(mb_handle* h, const float* in, float* out, const ConvW& w, i
     p.n_img = nb; p.H = R; p.W = R; p.Cin = w.cin; p.Cout = w.cout; p.taps = w.taps; p.stride = stride;
     p.bw = R >= 128 ? 128 : R; p.bh = 128 / p.bw;
     p.bias = w.bias; p.residual = residual;
+    // GroupNorm partials of the output for whichever GroupNorm reads it next (32 groups of Cout / 32 = 4, 8 or 16 channels)
+    const int cpg = w.cout / 32;
+    const bool fuse_gn = cpg == 4 || cpg == 8 || cpg == 16;
+    p.gn_part = fuse_gn ? h->gn_box : nullptr;
+    p.gn_cpg_log2 = cpg == 4 ? 2 : (cpg == 8 ? 3 : 4);
+    h->gn_box_src = fuse_gn ? out : nullptr;
     const uint64_t plane_w = stride == 2 ? (uint64_t)(Rin + 2) / 2 : (uint64_t)R + 2;
     const uint64_t adims[5] = {(uint64_t)w.cin, plane_w, plane_w, (uint64_t)nb, stride == 2 ? 4u : 1u};
     const uint32_t abox[5] = {64, (uint32_t)p.bw, (uint32_t)p.bh, 1, 1};
@@ -989,6 +1007,7 @@ static int decode_impl(mb_handle* h, const int64_t* tokens, int B, float* images
         const int nb = B - b0 < kDecChunk ? B - b0 : kDecChunk;
         float *X = h->dx, *T1 = h->dt1, *T2 = h->dt2;
         int R = P;
+        h->gn_box_src = nullptr;                                   // conv_in_tokens_kernel writes X without partials
         const long long total = (long long)nb * P * P * h->dec_c0;
         { ProfScope prof(h, MB_PROF_DEC_IO, st);
         conv_in_tokens_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tokens + (size_t)b0 * c.seq_len, h->cin_w, h->cin_b, X, nb, P, h->bits, h->dec_c0); }
@@ -1027,6 +1046,7 @@ static int encode_impl(mb_handle* h, const float* images, int B, float* z, int64
         const int nb = B - b0 < kDecChunk ? B - b0 : kDecChunk;
         float *X = h->dx, *T1 = h->dt1, *T2 = h->dt2;
         int R = Rimg;
+        h->gn_box_src = nullptr;                                   // enc_conv_in_kernel writes X without partials
         {
             ProfScope prof(h, MB_PROF_DEC_IO, st);
             const long long total = (long long)nb * R * R * (h->enc_c0 / 4);

@@ -82,6 +82,10 @@ struct ConvTcParams {
     int bw, bh;                         // pixel tile = bh rows x bw columns, bw * bh = 128
     const float* bias;                  // [Cout] or nullptr
     const float* residual;              // fp32 NHWC [n_img*H*W, Cout] or nullptr
+    float2* gn_part;                    // [n_img*H*W / 32][32] (sum, sumsq) of every 32-pixel x GroupNorm-group box of the OUTPUT, or
+                                        // nullptr: the statistics pass of the GroupNorm that consumes this conv's output
+                                        // (autoencoder.py:39-43, 32 groups) is fused here instead of re-reading the activation
+    int gn_cpg_log2;                    // log2(channels per group) = log2(Cout / 32): 2, 3 or 4
 };
 
 struct ConvTcCfg {
@@ -236,6 +240,24 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
                 if (lane == 0) {
                     tma_store_2d(&tm_out, stg, n0, (int)row0);
                     tma_store_commit();
+                }
+                if (p.gn_part) {
+                    // GroupNorm partials of the values as stored: lane = channel n0 + lane, summed over the box's 32 pixels from
+                    // the staging tile (a row's 16-byte chunks are XOR-swizzled by the row: one bank per lane, no conflicts),
+                    // then over the lanes of a group.  Fixed order -> run-to-run identical statistics.
+                    float s1 = 0.f, s2 = 0.f;
+                    const uint8_t* colp = stg + (lane & 3) * 4;
+#pragma unroll 8
+                    for (int r = 0; r < 32; ++r) {
+                        const float v = *reinterpret_cast<const float*>(colp + r * 128 + (((lane >> 2) ^ (r & 7)) << 4));
+                        s1 += v; s2 = fmaf(v, v, s2);
+                    }
+                    for (int o = 1; o < (1 << p.gn_cpg_log2); o <<= 1) {
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                    }
+                    if ((lane & ((1 << p.gn_cpg_log2) - 1)) == 0)
+                        p.gn_part[(size_t)(row0 >> 5) * 32 + ((n0 + lane) >> p.gn_cpg_log2)] = make_float2(s1, s2);
                 }
             }
             tc_fence_before();

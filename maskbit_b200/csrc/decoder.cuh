@@ -82,6 +82,29 @@ gn_partial_kernel(const float* __restrict__ x, double2* __restrict__ partial, in
     if (threadIdx.x < 32) partial[((size_t)n * chunks + chunk) * 32 + threadIdx.x] = make_double2(s_sum[threadIdx.x], s_sq[threadIdx.x]);
 }
 
+// The same partials from the per-box sums the convolution epilogue left behind (conv_tcgen05.cuh, ConvTcParams::gn_part):
+// part float2 [B * HW / 32][32]; one block per image, thread = (group, 1 of 8 interleaved box subsets), fp64 accumulation
+// in a fixed order.  Reads HW/32 * 256 B per image instead of the HW * C * 4 B activation.
+__global__ void __launch_bounds__(256)
+gn_reduce_kernel(const float2* __restrict__ part, double2* __restrict__ partial, int boxes_per_img) {
+    const int n = blockIdx.x, g = threadIdx.x & 31, sub = threadIdx.x >> 5;
+    const float2* base = part + (size_t)n * boxes_per_img * 32 + g;
+    double s = 0.0, q = 0.0;
+    for (int b = sub; b < boxes_per_img; b += 8) {
+        const float2 v = __ldg(base + (size_t)b * 32);
+        s += (double)v.x; q += (double)v.y;
+    }
+    __shared__ double sh_s[8][32], sh_q[8][32];
+    sh_s[sub][g] = s; sh_q[sub][g] = q;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double ts = 0.0, tq = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { ts += sh_s[k][g]; tq += sh_q[k][g]; }
+        partial[(size_t)n * 32 + g] = make_double2(ts, tq);
+    }
+}
+
 // scale[n][c] = rstd * gamma[c]; shift[n][c] = beta[c] - mean * rstd * gamma[c]
 __global__ void gn_finalize_kernel(const double2* __restrict__ partial, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift,
