@@ -952,8 +952,8 @@ static int run_conv(mb_handle* h, const float* in, float* out, const ConvW& w, i
     const int Rin = R * stride;                                     // size of the (upsampled) conv input
     {
         ProfScope prof(h, MB_PROF_DEC_IO, st);
-        const long long total = (long long)nb * (Rin + 2) * (Rin + 2) * (w.cin / 8);
-        act_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, gn ? h->gn_scale : nullptr, gn ? h->gn_shift : nullptr,
+        const dim3 agrid((unsigned)(((Rin + 2) * (w.cin / 8) + 255) / 256), (unsigned)(nb * (Rin + 2)));
+        act_split_kernel<<<agrid, 256, 0, st>>>(in, gn ? h->gn_scale : nullptr, gn ? h->gn_shift : nullptr,
                                                                           h->act_hi, h->act_lo, nb, Rin, Rin, w.cin, up, stride == 2 ? 4 : 1);
         CU_TRY(cudaGetLastError()); h->launches++;
     }

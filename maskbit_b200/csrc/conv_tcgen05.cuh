@@ -24,16 +24,17 @@ namespace mb {
 // scale / shift  [N][C] GroupNorm-apply coefficients or nullptr (no norm, no SiLU)
 // hi/lo bf16 [N, H+2, W+2, C], border = 0;  planes = 1
 //       or, planes = 4 (input of a stride-2 conv): [4][N, (H+2)/2, (W+2)/2, C], plane = (yp & 1) * 2 + (xp & 1) of padded (yp, xp)
+// grid = (ceil((W+2) * C/8 / 256), N * (H+2)): one padded row per blockIdx.y, so the only per-thread index arithmetic is one
+// 32-bit divide (the 64-bit div / mod chain of a flat index held this HBM-bound kernel at 43-60 % of the copy bandwidth).
 __global__ void __launch_bounds__(256)
 act_split_kernel(const float* __restrict__ in, const float* __restrict__ scale, const float* __restrict__ shift,
                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int N, int H, int W, int C, int up, int planes) {
     const int c8 = C >> 3;                                      // 8-channel groups per pixel
-    const long long total = (long long)N * (H + 2) * (W + 2) * c8;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int cg = (int)(idx % c8);
-    const long long pp = idx / c8;
-    const int xp = (int)(pp % (W + 2)), yp = (int)((pp / (W + 2)) % (H + 2)), n = (int)(pp / ((long long)(W + 2) * (H + 2)));
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;        // position inside the padded row
+    if (i >= (W + 2) * c8) return;
+    const int xp = i / c8, cg = i - xp * c8;
+    const int n = blockIdx.y / (H + 2), yp = blockIdx.y - n * (H + 2);
+    const long long idx = ((long long)blockIdx.y * (W + 2) + xp) * c8 + cg;
     uint4 oh = make_uint4(0, 0, 0, 0), ol = make_uint4(0, 0, 0, 0);
     if (xp >= 1 && xp <= W && yp >= 1 && yp <= H) {
         const int Hin = H >> up, Win = W >> up;
@@ -50,7 +51,7 @@ act_split_kernel(const float* __restrict__ in, const float* __restrict__ scale, 
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float t = fmaf(v[i], s[i], h[i]);
-                v[i] = t / (1.0f + __expf(-t));                   // SiLU
+                v[i] = __fdividef(t, 1.0f + __expf(-t));          // SiLU
             }
         }
         uint32_t wh[4], wl[4];
