@@ -624,7 +624,7 @@ static int set_gemm_attr_bn() {
 }
 template <int EPI>
 static int set_gemm2_attr() {
-    CU_TRY(cudaFuncSetAttribute(gemm2_bf16_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(gemm2_bf16_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm2_smem_bytes(EPI)));
     return 0;
 }
 // CTA-pair (cta_group::2) GEMM for every N % 256 == 0 Linear; MASKBIT_B200_GEMM_2CTA=0 selects the 1-CTA kernel (A/B timing)
@@ -678,23 +678,23 @@ static int launch_gemm_bn(mb_handle* h, const CUtensorMap& ta, const CUtensorMap
     if (h) h->launches++;
     return 0;
 }
-static int launch_gemm2(mb_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
-                        int epi, int num_sms, cudaStream_t st) {
+static int launch_gemm2(mb_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
+                        const GemmParams& p, int epi, int num_sms, cudaStream_t st) {
     const int tiles = ((p.M + 255) / 256) * (p.N / 256);
     int pairs = num_sms / 2;
     if (tiles < pairs) pairs = tiles;
-    const int grid = 2 * pairs, smem = Gemm2Cfg::SMEM_BYTES;
+    const int grid = 2 * pairs, smem = gemm2_smem_bytes(epi);
     switch (epi) {
-        case 0: gemm2_bf16_tcgen05_kernel<0><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, p); break;
-        case 1: gemm2_bf16_tcgen05_kernel<1><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, p); break;
-        case 2: gemm2_bf16_tcgen05_kernel<2><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, p); break;
-        case 3: gemm2_bf16_tcgen05_kernel<3><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, p); break;
-        case 4: gemm2_bf16_tcgen05_kernel<4><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, p); break;
-        case 5: gemm2_bf16_tcgen05_kernel<5><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, p); break;
-        case 6: gemm2_bf16_tcgen05_kernel<6><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, p); break;
-        case 7: gemm2_bf16_tcgen05_kernel<7><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, p); break;
-        case 8: gemm2_bf16_tcgen05_kernel<8><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, p); break;
-        case 9: gemm2_bf16_tcgen05_kernel<9><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, p); break;
+        case 0: gemm2_bf16_tcgen05_kernel<0><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, tr, p); break;
+        case 1: gemm2_bf16_tcgen05_kernel<1><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, tr, p); break;
+        case 2: gemm2_bf16_tcgen05_kernel<2><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, tr, p); break;
+        case 3: gemm2_bf16_tcgen05_kernel<3><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, tr, p); break;
+        case 4: gemm2_bf16_tcgen05_kernel<4><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, tr, p); break;
+        case 5: gemm2_bf16_tcgen05_kernel<5><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, tr, p); break;
+        case 6: gemm2_bf16_tcgen05_kernel<6><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, tr, p); break;
+        case 7: gemm2_bf16_tcgen05_kernel<7><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, tr, p); break;
+        case 8: gemm2_bf16_tcgen05_kernel<8><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, tr, p); break;
+        case 9: gemm2_bf16_tcgen05_kernel<9><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, tr, p); break;
         default: return fail(MB_ERR_INVALID, "bad epilogue %d", epi);
     }
     CU_TRY(cudaGetLastError());
@@ -703,12 +703,14 @@ static int launch_gemm2(mb_handle* h, const CUtensorMap& ta, const CUtensorMap& 
 }
 // tb_half: the weight's tensor map with a 128-row box (CTA-pair kernel: each CTA stages half of the 256-row B tile)
 // tc: output tensor map (box 64 x 32) for the bf16-output epilogues of the CTA-pair kernel
+// tr: the residual tensor's map (box 64 x 32, like tc) for the residual epilogue of the CTA-pair kernel
 static int launch_gemm(mb_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tb_half, const CUtensorMap* tc,
-                       int BN, const GemmParams& p, int epi, int num_sms, cudaStream_t st) {
-    if (g_use_2cta && tb_half && (tc || !gemm2_tma_store(epi)) && BN == 256 && p.K % 64 == 0 && p.N % 256 == 0 && num_sms >= 2) {
+                       int BN, const GemmParams& p, int epi, int num_sms, cudaStream_t st, const CUtensorMap* tr = nullptr) {
+    if (g_use_2cta && tb_half && (tc || !gemm2_tma_store(epi)) && (tr || !gemm2_res_tma(epi)) && BN == 256 && p.K % 64 == 0 &&
+        p.N % 256 == 0 && num_sms >= 2) {
         if ((epi == EPI_RES_LN_BF16_STATS || epi == EPI_LNIN_GELU_BF16_STATS) && p.N != 64 * LN_PARTIALS)
             return fail(MB_ERR_INVALID, "row-statistics epilogue needs N=%d (got N=%d)", 64 * LN_PARTIALS, p.N);
-        return launch_gemm2(h, ta, *tb_half, tc ? *tc : ta, p, epi, num_sms, st);
+        return launch_gemm2(h, ta, *tb_half, tc ? *tc : ta, tr ? *tr : ta, p, epi, num_sms, st);
     }
     if (p.K % 64 || p.N % BN) return fail(MB_ERR_INVALID, "gemm shape M=%d N=%d K=%d BN=%d", p.M, p.N, p.K, BN);
     if ((epi == EPI_RES_LN_BF16_STATS || epi == EPI_LNIN_GELU_BF16_STATS) && (BN != 256 || p.N != 64 * LN_PARTIALS))
@@ -720,13 +722,13 @@ static int launch_gemm(mb_handle* h, const CUtensorMap& ta, const CUtensorMap& t
 }
 static int run_linear(mb_handle* h, int kind, const CUtensorMap& ta, const Linear& L, int M, int epi, const __nv_bfloat16* residual,
                       const float2* stats_in, float2* stats_out, void* out, const CUtensorMap* tm_out, int ldo, cudaStream_t st,
-                      int seq_in = 0, int seq_out = 0) {
+                      int seq_in = 0, int seq_out = 0, const CUtensorMap* tm_res = nullptr) {
     ProfScope prof(h, kind, st);
     GemmParams p;
     p.M = M; p.N = L.N; p.K = L.K; p.bias = L.b; p.vec2 = L.v2; p.residual = residual; p.ldr = L.N;
     p.stats_in = stats_in; p.stats_out = stats_out; p.inv_d = 1.0f / (float)h->cfg.hidden_dim; p.eps = 1e-12f;
     p.out = out; p.ldo = ldo; p.seq_in = seq_in; p.seq_out = seq_out;
-    return launch_gemm(h, ta, L.tm, L.BN == 256 ? &L.tm_half : nullptr, tm_out, L.BN, p, epi, h->num_sms, st);
+    return launch_gemm(h, ta, L.tm, L.BN == 256 ? &L.tm_half : nullptr, tm_out, L.BN, p, epi, h->num_sms, st, tm_res);
 }
 
 // ------------------------------------------------------------------------------------------------ generator forward
@@ -811,10 +813,10 @@ static int forward_impl(mb_handle* h, const int64_t* tokens, int n_token_rows, c
         // attention block (bert.py:137-139): yB = out_proj(MHA(LN(yA))) + LN(yA)
         MB_TRY(run_linear(h, MB_PROF_GEMM_QKV, h->tm_yA, L.qkv, M, EPI_LNIN_BF16, nullptr, h->stA, nullptr, h->qkv, &h->tmo_qkv, 3 * D, st));
         MB_TRY(run_attention(h, h->tm_qkv_big, h->tm_qkv_row, h->tmo_att, h->qkv, h->att, n_seq, h->S, D, c.heads, h->num_sms, st));
-        MB_TRY(run_linear(h, MB_PROF_GEMM_OUT, h->tm_att, L.out, M, EPI_RES_LN_BF16_STATS, h->yA, res_stA, h->stB, h->yB, &h->tmo_yB, D, st));
+        MB_TRY(run_linear(h, MB_PROF_GEMM_OUT, h->tm_att, L.out, M, EPI_RES_LN_BF16_STATS, h->yA, res_stA, h->stB, h->yB, &h->tmo_yB, D, st, 0, 0, &h->tmo_yA));
         // feed-forward block (bert.py:69-70): yA = W2 gelu(W1 LN1(yB) + b1) + b2 + LN1(yB)
         MB_TRY(run_linear(h, MB_PROF_GEMM_UP, h->tm_yB, L.up, M, EPI_LNIN_GELU_BF16, nullptr, h->stB, nullptr, h->hmid, &h->tmo_hmid, c.mlp_dim, st));
-        MB_TRY(run_linear(h, MB_PROF_GEMM_DOWN, h->tm_hmid, L.down, M, EPI_RES_LN_BF16_STATS, h->yB, res_stB, h->stA, h->yA, &h->tmo_yA, D, st));
+        MB_TRY(run_linear(h, MB_PROF_GEMM_DOWN, h->tm_hmid, L.down, M, EPI_RES_LN_BF16_STATS, h->yB, res_stB, h->stA, h->yA, &h->tmo_yA, D, st, 0, 0, &h->tmo_yB));
     }
     // head (bert.py:500-503): LN(gelu(W LN2(yA) + b)) -> prediction layer, class-token row dropped
     MB_TRY(run_linear(h, MB_PROF_GEMM_HEAD, h->tm_yA, h->head, M, EPI_LNIN_GELU_BF16_STATS, nullptr, h->stA, h->stB, h->yB, &h->tmo_yB, D, st));
@@ -1172,18 +1174,20 @@ extern "C" int mb_test_gemm_ex(const uint16_t* A, const uint16_t* W, const float
     MB_TRY(init_kernel_attrs());
     const int BN = pick_bn(N);
     if (!BN) return fail(MB_ERR_INVALID, "N=%d not tileable", N);
-    CUtensorMap ta, tb, tbh, tc;
+    CUtensorMap ta, tb, tbh, tc, tr;
     MB_TRY(make_tmap_bf16(&ta, A, M, K, 128));
     MB_TRY(make_tmap_bf16(&tb, W, N, K, BN));
     if (BN == 256) MB_TRY(make_tmap_bf16(&tbh, W, N, K, 128));
     const bool bf16_out = gemm2_tma_store(epi);
     if (BN == 256 && bf16_out) MB_TRY(make_tmap_out(&tc, out, M, N));
+    const bool res_map = BN == 256 && residual && gemm2_res_tma(epi);
+    if (res_map) MB_TRY(make_tmap_out(&tr, residual, M, N));
     GemmParams p;
     p.M = M; p.N = N; p.K = K; p.bias = bias; p.vec2 = vec2; p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = N;
     p.stats_in = reinterpret_cast<const float2*>(stats_in); p.stats_out = reinterpret_cast<float2*>(stats_out);
     p.inv_d = inv_d; p.eps = eps; p.out = out; p.ldo = N; p.seq_in = seq_in; p.seq_out = seq_out; p.trace = g_gemm_trace;
     return launch_gemm(nullptr, ta, tb, BN == 256 ? &tbh : nullptr, (BN == 256 && bf16_out) ? &tc : nullptr, BN, p, epi, test_num_sms(),
-                       (cudaStream_t)stream);
+                       (cudaStream_t)stream, res_map ? &tr : nullptr);
 }
 extern "C" int mb_test_gemm(const uint16_t* A, const uint16_t* W, const float* bias, const uint16_t* residual, void* out, int M,
                             int N, int K, int epi, int seq_in, int seq_out, mb_stream stream) {

@@ -269,7 +269,9 @@ struct EpiStage {
 // svec: the tile's per-column vectors staged in shared memory ([BN] bias | [BN] vec2), or nullptr to read them from global.
 // With ~225 KB of the SM's 228 KB carved out as shared memory there is no L1 left: every __ldg of bias / u / gamma is an L2
 // round trip issued after the accumulator wait, and those round trips (not arithmetic) were most of the epilogue's time.
-template <int BN, int EPI, bool kTma = false, int NSPLIT = 2, bool kPre = false, bool kSV = false>
+// kResS: the residual rows were loaded by TMA into the staging tiles (stg.buf + 4096 * (64-column pair), 128B swizzle); each
+// thread reads its row's 64 bytes of a chunk and later writes the chunk's results over them, then the pair is TMA-stored.
+template <int BN, int EPI, bool kTma = false, int NSPLIT = 2, bool kPre = false, bool kSV = false, bool kResS = false>
 __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, uint32_t taddr, int n_blk, int half,
                                         EpiStage stg = EpiStage{nullptr, nullptr, 0}, const uint4* res = nullptr,
                                         const float* svec = nullptr) {
@@ -320,7 +322,10 @@ __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, u
                 const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + n0);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const uint4 r4 = kPre ? res[(c >> 3) + j] : __ldg(rp + j);
+                    uint4 r4;
+                    if (kResS) r4 = *reinterpret_cast<const uint4*>(stg.buf + (c >> 6) * 4096 + (threadIdx.x & 31) * 128 +
+                                                                   (((((c >> 5) & 1) * 4 + j) ^ (threadIdx.x & 7)) << 4));
+                    else r4 = kPre ? res[(c >> 3) + j] : __ldg(rp + j);
                     const uint32_t w[4] = {r4.x, r4.y, r4.z, r4.w};
                     if (EPI == EPI_RES_LN_BF16_STATS) {   // + ((y - mean) * rstd) * gamma   (beta is folded into p.bias)
                         const float4 g0 = kSV ? *reinterpret_cast<const float4*>(svec + BN + col0 + j * 8)
@@ -359,11 +364,11 @@ __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, u
             if (kTma) {
                 const int lane = threadIdx.x & 31;
                 const int sub = (c >> 5) & 1;                 // which 32-column half of the 64-column staging row
-                if (sub == 0) {                               // the previous store must have finished reading the buffer
+                if (sub == 0 && !kResS) {                     // the previous store must have finished reading the buffer
                     if (lane == 0) tma_store_wait_read<0>();
                     __syncwarp();
                 }
-                uint8_t* rowp = stg.buf + lane * 128;
+                uint8_t* rowp = stg.buf + (kResS ? (c >> 6) * 4096 : 0) + lane * 128;
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     *reinterpret_cast<uint4*>(rowp + (((sub * 4 + j) ^ (lane & 7)) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
@@ -371,7 +376,7 @@ __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, u
                     fence_async_proxy();                      // generic-proxy smem writes -> visible to the bulk copy
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_2d(stg.tm, stg.buf, n0 - 32, stg.row0);
+                        tma_store_2d(stg.tm, stg.buf + (kResS ? (c >> 6) * 4096 : 0), n0 - 32, stg.row0);
                         tma_store_commit();
                     }
                 }
@@ -511,8 +516,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 //   by 8 warps;
 //   tcgen05.commit multicasts the "stage consumed" / "accumulator ready" arrivals to both CTAs; the epilogue warps of both
 //   CTAs release the accumulator stage on the leader's tmem_empty barrier.
-struct Gemm2Cfg {
-    static constexpr int BM = 256, BN = 256, BK = 64, STAGES = GEMM2_STAGES;
+// kResTma (residual epilogue): the residual rows arrive by TMA in the epilogue's own staging tiles (two 64-column tiles per warp,
+// results written over them in place), paid for with one pipeline stage.
+template <bool kResTma>
+struct Gemm2CfgT {
+    static constexpr int BM = 256, BN = 256, BK = 64, STAGES = kResTma ? 5 : GEMM2_STAGES;
     // 4 TMEM lane quarters x 2 column halves.  16 warps (4 x 4, 5 stages to make room for their staging) measured SLOWER on
     // every GEMM (QKV 1435 -> 1249, up 1272 -> 1146 TFLOP/s): the extra warps and the lost stage cost more than the added
     // epilogue parallelism buys.
@@ -520,15 +528,22 @@ struct Gemm2Cfg {
     static constexpr int THREADS = 128 + EPI_WARPS * 32;
     static constexpr int A_BYTES = 128 * BK * 2;      // per CTA
     static constexpr int B_BYTES = 128 * BK * 2;      // per CTA (half of the 256 weight rows)
-    static constexpr int STG_BYTES = EPI_WARPS * 4096; // output staging: per epilogue warp 32 rows x 128 B
+    static constexpr int STG_WARP = kResTma ? 8192 : 4096;   // per epilogue warp: 32 rows x 128 B (x 2 column pairs with kResTma)
+    static constexpr int STG_BYTES = EPI_WARPS * STG_WARP;   // output staging
     static constexpr int VEC_BYTES = 2 * BN * 4;       // the tile's per-column epilogue vectors: [BN] bias | [BN] vec2
-    static constexpr int BAR_BYTES = 192;              // 2*STAGES + 4 mbarriers + the TMEM base slot
+    static constexpr int BAR_BYTES = 256;              // 2*STAGES + 4 (+ EPI_WARPS residual) mbarriers + the TMEM base slot
     // The dynamic shared-memory window is 1024-byte aligned (declared so, and checked at kernel entry): no alignment slack,
     // which is what leaves room for VEC_BYTES next to six pipeline stages (232 448 B limit).
     static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + STG_BYTES + VEC_BYTES + BAR_BYTES;
     static_assert(SMEM_BYTES <= 232448, "CTA-pair GEMM shared memory over the 227 KB limit");
-    static_assert((2 * STAGES + 4) * 8 + 4 <= BAR_BYTES, "barrier area too small");
+    static_assert((2 * STAGES + 4 + EPI_WARPS) * 8 + 4 <= BAR_BYTES, "barrier area too small");
 };
+using Gemm2Cfg = Gemm2CfgT<false>;
+#ifndef GEMM2_RES_TMA
+#define GEMM2_RES_TMA 1          // residual epilogue of the CTA-pair kernel: residual rows by TMA into the staging tiles (else LDG.256)
+#endif
+__host__ __device__ constexpr bool gemm2_res_tma(int epi) { return GEMM2_RES_TMA && epi == EPI_RES_LN_BF16_STATS; }
+__host__ __device__ constexpr int gemm2_smem_bytes(int epi) { return gemm2_res_tma(epi) ? Gemm2CfgT<true>::SMEM_BYTES : Gemm2CfgT<false>::SMEM_BYTES; }
 // bf16-output epilogues of the CTA-pair kernel go through shared memory and TMA stores
 #ifndef GEMM2_DIRECT256
 #define GEMM2_DIRECT256 0   // 1: CTA-pair kernel stores straight from registers with 256-bit stores instead of smem + TMA
@@ -541,8 +556,9 @@ __host__ __device__ constexpr bool gemm2_tma_store(int epi) {
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg::THREADS, 1)
 gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                          const __grid_constant__ CUtensorMap tm_c, GemmParams p) {
-    using C = Gemm2Cfg;
+                          const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_r, GemmParams p) {
+    constexpr bool kResTma = gemm2_res_tma(EPI);     // tm_r: the residual tensor, box {64 columns, 32 rows} like tm_c
+    using C = Gemm2CfgT<kResTma>;
     constexpr int BN = C::BN, BK = C::BK, STAGES = C::STAGES;
     constexpr bool kTma = gemm2_tma_store(EPI);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -557,7 +573,8 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
     uint64_t* empty = bars + STAGES;                // per CTA, arrived by the leader's multicast commit
     uint64_t* tmem_full = bars + 2 * STAGES;        // per CTA, arrived by the leader's multicast commit
     uint64_t* tmem_empty = bars + 2 * STAGES + 2;   // leader only: 8 epilogue warps of each CTA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* res_full = bars + 2 * STAGES + 4;     // kResTma: per epilogue warp, the tile's residual boxes have landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + C::EPI_WARPS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // Warp roles.  The SM's warp schedulers favour the highest warp id among eligible warps, so with GEMM2_ROLES_HIGH the
@@ -575,10 +592,12 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
         tma_prefetch_desc(&tm_a);
         tma_prefetch_desc(&tm_b);
         if (kTma) tma_prefetch_desc(&tm_c);
+        if (kResTma) tma_prefetch_desc(&tm_r);
     }
     if (warp == W_MMA && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 2 * C::EPI_WARPS); }
+        for (int s = 0; s < C::EPI_WARPS; ++s) mbar_init(&res_full[s], 1);
         fence_mbar_init();
     }
     if (warp == W_ALLOC) tmem_alloc_2sm<512>(tmem_slot);
@@ -672,17 +691,28 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
             const int row0 = m_blk * C::BM + (int)rank * 128 + quarter * 32;
             const EpiRow er = epi_prepare<EPI>(p, row0 + lane);
             constexpr int CPW = BN / (C::EPI_WARPS / 4);
-            constexpr bool kPre = GEMM_RES_PREFETCH && EPI == EPI_RES_LN_BF16_STATS;
+            constexpr bool kPre = GEMM_RES_PREFETCH && EPI == EPI_RES_LN_BF16_STATS && !kResTma;
             ResSlab<kPre ? CPW : 8> slab;
             if constexpr (kPre) epi_load_residual<CPW>(p, er, n_blk * BN + half * CPW, slab);
+            uint8_t* stg_w = smem_stg + ew * C::STG_WARP;
+            if constexpr (kResTma) {
+                // the previous tile's two stores have read the staging tiles -> refill them with this tile's residual rows
+                if (lane == 0) {
+                    tma_store_wait_read<0>();
+                    mbar_arrive_expect_tx(&res_full[ew], 2 * 4096);
+                    tma_load_2d(stg_w, &tm_r, &res_full[ew], n_blk * BN + half * CPW, row0);
+                    tma_load_2d(stg_w + 4096, &tm_r, &res_full[ew], n_blk * BN + half * CPW + 64, row0);
+                }
+                __syncwarp();
+            }
             if (ew == 0 && lane == 0) GEMM_EV(1, 0, it, clock64());
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
             if (ew == 0 && lane == 0) GEMM_EV(1, 1, it, clock64());
+            if constexpr (kResTma) mbar_wait(&res_full[ew], it & 1);
             if (!GEMM_TIMING_NO_EPI)
-            epi_run<BN, EPI, kTma, C::EPI_WARPS / 4, kPre, true>(p, er, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN,
-                                                                 n_blk, half, EpiStage{smem_stg + ew * 4096, &tm_c, row0}, slab.v,
-                                                                 smem_vec);
+            epi_run<BN, EPI, kTma, C::EPI_WARPS / 4, kPre, true, kResTma>(p, er, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN,
+                                                                          n_blk, half, EpiStage{stg_w, &tm_c, row0}, slab.v, smem_vec);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tmem_empty[as]), 0));
