@@ -174,7 +174,7 @@ int mb_profile_read(mb_handle* h, double* ms, int64_t* counts, int n_kinds);
  * 3 bias->f32 with class-row drop (seq_in/seq_out), 4 bias+gelu->f32 */
 int mb_test_gemm(const uint16_t* A, const uint16_t* W, const float* bias, const uint16_t* residual, void* out, int M, int N,
                  int K, int epi, int seq_in, int seq_out, mb_stream stream);
-/* LayerNorm-folded epilogues (csrc/gemm_tcgen05.cuh): stats_in / stats_out float [M][16][2] partial (sum, sumsq) per row;
+/* LayerNorm-folded epilogues (csrc/gemm_tcgen05.cuh): stats_in / stats_out float [M][8][2] partial (sum, sumsq) per row;
  * epi 5: rstd*(acc - mean*vec2) + bias -> bf16; 6: gelu of that -> bf16; 7: acc + bias + ((res - mean)*rstd)*vec2 -> bf16 + stats_out;
  * 8: like 6 + stats_out; 9: like 5 -> f32 with class-row drop.  mean / rstd come from stats_in with width 1/inv_d and eps. */
 int mb_test_gemm_ex(const uint16_t* A, const uint16_t* W, const float* bias, const float* vec2, const uint16_t* residual,

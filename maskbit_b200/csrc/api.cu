@@ -708,13 +708,13 @@ static int launch_gemm(mb_handle* h, const CUtensorMap& ta, const CUtensorMap& t
                        int BN, const GemmParams& p, int epi, int num_sms, cudaStream_t st, const CUtensorMap* tr = nullptr) {
     if (g_use_2cta && tb_half && (tc || !gemm2_tma_store(epi)) && (tr || !gemm2_res_tma(epi)) && BN == 256 && p.K % 64 == 0 &&
         p.N % 256 == 0 && num_sms >= 2) {
-        if ((epi == EPI_RES_LN_BF16_STATS || epi == EPI_LNIN_GELU_BF16_STATS) && p.N != 64 * LN_PARTIALS)
-            return fail(MB_ERR_INVALID, "row-statistics epilogue needs N=%d (got N=%d)", 64 * LN_PARTIALS, p.N);
+        if ((epi == EPI_RES_LN_BF16_STATS || epi == EPI_LNIN_GELU_BF16_STATS) && p.N != 128 * LN_PARTIALS)
+            return fail(MB_ERR_INVALID, "row-statistics epilogue needs N=%d (got N=%d)", 128 * LN_PARTIALS, p.N);
         return launch_gemm2(h, ta, *tb_half, tc ? *tc : ta, tr ? *tr : ta, p, epi, num_sms, st);
     }
     if (p.K % 64 || p.N % BN) return fail(MB_ERR_INVALID, "gemm shape M=%d N=%d K=%d BN=%d", p.M, p.N, p.K, BN);
-    if ((epi == EPI_RES_LN_BF16_STATS || epi == EPI_LNIN_GELU_BF16_STATS) && (BN != 256 || p.N != 64 * LN_PARTIALS))
-        return fail(MB_ERR_INVALID, "row-statistics epilogue needs N=%d, BN=256 (got N=%d BN=%d)", 64 * LN_PARTIALS, p.N, BN);
+    if ((epi == EPI_RES_LN_BF16_STATS || epi == EPI_LNIN_GELU_BF16_STATS) && (BN != 256 || p.N != 128 * LN_PARTIALS))
+        return fail(MB_ERR_INVALID, "row-statistics epilogue needs N=%d, BN=256 (got N=%d BN=%d)", 128 * LN_PARTIALS, p.N, BN);
     if (BN == 256) return launch_gemm_bn<256>(h, ta, tb, p, epi, num_sms, st);
     if (BN == 128) return launch_gemm_bn<128>(h, ta, tb, p, epi, num_sms, st);
     if (BN == 64) return launch_gemm_bn<64>(h, ta, tb, p, epi, num_sms, st);

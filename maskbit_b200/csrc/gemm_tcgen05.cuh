@@ -79,7 +79,7 @@ enum EpiMode : int {
     EPI_LNIN_F32_SEQ = 9,         // out fp32 = rstd*(acc - mean*u) + c, class row dropped            (prediction layer)
 };
 constexpr int GEMM_NUM_EPI = 10;
-constexpr int LN_PARTIALS = 16;   // partial (sum, sumsq) slots per row: one per 64-column block of a 1024-wide row
+constexpr int LN_PARTIALS = 8;    // partial (sum, sumsq) slots per row: one per 128-column epilogue-warp slab of a 1024-wide row
 
 struct GemmParams {
     int M, N, K;
@@ -399,11 +399,10 @@ __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, u
 #pragma unroll 1
         for (int c = 0; c < COLS_PER_WARP; c += 32) chunk(c);
     }
-    if (kStats && row_ok && !GEMM_TIMING_NO_STATS) {   // slot = 64-column block index of the warp's first column; a wider warp slab zeroes the slots it spans
-        float2* so = p.stats_out + (size_t)row * LN_PARTIALS + (n_blk * BN + half * COLS_PER_WARP) / 64;
+    if (kStats && row_ok && !GEMM_TIMING_NO_STATS) {   // slot = index of the warp's 128-column slab in the 1024-wide row
+        // (launches with a narrower warp slab are rejected on the host: launch_gemm requires BN == 256 for the STATS epilogues)
+        float2* so = p.stats_out + (size_t)row * LN_PARTIALS + (n_blk * BN + half * COLS_PER_WARP) / 128;
         so[0] = make_float2(st_sum + st_sum1, st_sq + st_sq1);
-#pragma unroll
-        for (int i = 1; i < COLS_PER_WARP / 64; ++i) so[i] = make_float2(0.f, 0.f);
     }
 }
 

@@ -105,8 +105,8 @@ def test_attention(n_seq, S):
 
 
 def _row_stats(y_bf16):
-    """[M][16][2] partial (sum, sumsq) statistics in the layout the kernels use: slot = 64-column block of the 1024-wide row."""
-    y = y_bf16.float().view(y_bf16.shape[0], 16, 64)
+    """[M][8][2] partial (sum, sumsq) statistics in the layout the kernels use: slot = 128-column slab of the 1024-wide row."""
+    y = y_bf16.float().view(y_bf16.shape[0], 8, 128)
     return torch.stack([y.sum(-1), (y * y).sum(-1)], dim=-1).contiguous()
 
 
@@ -117,7 +117,7 @@ def _gemm_ex(a, w, bias, vec2, residual, stats_in, epi, want_stats, seq_in=0, se
         out = torch.full(((M // seq_in) * seq_out, N), float("nan"), dtype=torch.float32, device="cuda")
     else:
         out = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
-    stats_out = torch.full((M, 16, 2), float("nan"), device="cuda") if want_stats else None
+    stats_out = torch.full((M, 8, 2), float("nan"), device="cuda") if want_stats else None
     _lib.check(_lib.lib().mb_test_gemm_ex(_p(a), _p(w), _p(bias), _p(vec2), _p(residual), _p(stats_in), _p(stats_out), _p(out), M, N, K,
                                           epi, seq_in, seq_out, 1.0 / 1024, eps, _stream()))
     torch.cuda.synchronize()
@@ -197,7 +197,7 @@ def test_gemm_stats_epilogue_rejects_other_widths():
     a = torch.zeros((128, 1024), dtype=torch.bfloat16, device="cuda")
     w = torch.zeros((512, 1024), dtype=torch.bfloat16, device="cuda")
     z = torch.zeros((512,), device="cuda")
-    st = torch.zeros((128, 16, 2), device="cuda")
+    st = torch.zeros((128, 8, 2), device="cuda")
     out = torch.zeros((128, 512), dtype=torch.bfloat16, device="cuda")
     rc = _lib.lib().mb_test_gemm_ex(_p(a), _p(w), _p(z), _p(z), _p(a), _p(st), _p(st), _p(out), 128, 512, 1024, 7, 0, 0, 1.0 / 1024, 1e-12, _stream())
     assert rc == -1 and b"row-statistics" in _lib.lib().mb_last_error()

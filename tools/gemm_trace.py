@@ -29,9 +29,9 @@ def main():
         bias = torch.randn((N,), device="cuda", generator=g)
         vec2 = torch.randn((N,), device="cuda", generator=g)
         res = torch.randn((M, N), device="cuda", generator=g).to(torch.bfloat16) if epi == 7 else None
-        stats = torch.rand((M, 16, 2), device="cuda", generator=g) + 1.0
+        stats = torch.rand((M, 8, 2), device="cuda", generator=g) + 1.0
         stats[:, :, 1] += 20.0
-        sto = torch.empty((M, 16, 2), device="cuda") if epi == 7 else None
+        sto = torch.empty((M, 8, 2), device="cuda") if epi == 7 else None
         out = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
         for _ in range(3):
             tr.zero_()

@@ -53,9 +53,9 @@ def main():
         bias = torch.randn((N,), device="cuda", generator=g)
         vec2 = torch.randn((N,), device="cuda", generator=g)
         res = torch.randn((M, N), device="cuda", generator=g).to(torch.bfloat16) if epi == 7 else None
-        stats = torch.rand((M, 16, 2), device="cuda", generator=g) + 1.0
+        stats = torch.rand((M, 8, 2), device="cuda", generator=g) + 1.0
         stats[:, :, 1] += 20.0
-        sto = torch.empty((M, 16, 2), device="cuda") if epi in (7, 8) else None
+        sto = torch.empty((M, 8, 2), device="cuda") if epi in (7, 8) else None
         out = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
         ms = timeit(lambda: _lib.check(L.mb_test_gemm_ex(p(A), p(W), p(bias), p(vec2), p(res), p(stats), p(sto), p(out), M, N, K, epi, 0, 0,
                                                          1.0 / 1024, 1e-12, st)), a.iters, flush)

@@ -31,18 +31,18 @@ def main():
     w2 = (torch.randn((D, H), device="cuda", generator=g) * 0.03).to(torch.bfloat16)
     b1, u1 = torch.randn((H,), device="cuda", generator=g), torch.randn((H,), device="cuda", generator=g)
     b2, g2 = torch.randn((D,), device="cuda", generator=g), torch.randn((D,), device="cuda", generator=g)
-    stats = torch.rand((M, 16, 2), device="cuda", generator=g) + 1.0
+    stats = torch.rand((M, 8, 2), device="cuda", generator=g) + 1.0
     stats[:, :, 1] += 20.0
-    sto = torch.empty((M, 16, 2), device="cuda")
+    sto = torch.empty((M, 8, 2), device="cuda")
     out = torch.empty((M, D), dtype=torch.bfloat16, device="cuda")
     hidden = torch.empty((M, H), dtype=torch.bfloat16, device="cuda")
 
     def mlp(rows0, rows, hid, hid_off_rows):
         # up: A = y[rows0:rows0+rows], LN-in + GELU -> hid ; down: A = hid, residual y rows, -> out rows
-        _lib.check(L.mb_test_gemm_ex(vp(y, rows0 * D * 2), vp(w1), vp(b1), vp(u1), None, vp(stats, rows0 * 128), None,
+        _lib.check(L.mb_test_gemm_ex(vp(y, rows0 * D * 2), vp(w1), vp(b1), vp(u1), None, vp(stats, rows0 * 64), None,
                                      vp(hid, hid_off_rows * H * 2), rows, H, D, 6, 0, 0, 1.0 / 1024, 1e-12, st))
-        _lib.check(L.mb_test_gemm_ex(vp(hid, hid_off_rows * H * 2), vp(w2), vp(b2), vp(g2), vp(y, rows0 * D * 2), vp(stats, rows0 * 128),
-                                     vp(sto, rows0 * 128), vp(out, rows0 * D * 2), rows, D, H, 7, 0, 0, 1.0 / 1024, 1e-12, st))
+        _lib.check(L.mb_test_gemm_ex(vp(hid, hid_off_rows * H * 2), vp(w2), vp(b2), vp(g2), vp(y, rows0 * D * 2), vp(stats, rows0 * 64),
+                                     vp(sto, rows0 * 64), vp(out, rows0 * D * 2), rows, D, H, 7, 0, 0, 1.0 / 1024, 1e-12, st))
 
     def run_full():
         mlp(0, M, hidden, 0)
