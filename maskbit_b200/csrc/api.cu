@@ -230,6 +230,14 @@ struct mb_handle {
     int drop_layout_B = 0;   // batch the drop flags in drop_ws are currently laid out for ([0]*B then [1]*B)
     int64_t *tok_a = nullptr, *tok_b = nullptr, *pred_buf = nullptr, *combined = nullptr;
     float* logits_ws = nullptr; uint8_t* drop_ws = nullptr;
+    int64_t* labels_ws = nullptr;        // the call's labels, copied so that captured forwards read a stable address
+    // Small batches are bound by the host's launch rate (122 launches per forward, ~15 us each on the host against ~8 us of
+    // GPU time at B = 1): mb_sample replays each forward as a CUDA graph, captured once per (sequence count, token buffer)
+    // on a stream of the handle's own (stream capture is not allowed on the legacy default stream a caller may pass).
+    struct FwdGraph { cudaGraphExec_t exec; int B, n_seq; const int64_t* tokens; int64_t nodes; };
+    std::vector<FwdGraph> fwd_graphs;
+    cudaStream_t gstream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     // decoder
     float *cin_w = nullptr, *cin_b = nullptr, *cout_w = nullptr, *cout_b = nullptr;
     int dec_c0 = 0, dec_cl = 0;
@@ -310,13 +318,20 @@ extern "C" int mb_create(const mb_config* cfg, mb_handle** out) {
     return 0;
 }
 
+static void drop_graphs(mb_handle* h) {   // captured forwards hold workspace addresses: gone with any reallocation
+    for (auto& g : h->fwd_graphs) cudaGraphExecDestroy(g.exec);
+    h->fwd_graphs.clear();
+}
 static void free_ws(mb_handle* h) {
+    drop_graphs(h);
     void* ps[] = {h->yA, h->yB, h->qkv, h->att, h->hmid, h->stA, h->stB};
     for (void* p : ps) if (p) cudaFree(p);
     h->yA = h->yB = h->qkv = h->att = h->hmid = nullptr; h->stA = h->stB = nullptr; h->cap_seqs = 0;
 }
 static void free_sample_ws(mb_handle* h) {
-    void* ps[] = {h->tok_a, h->tok_b, h->pred_buf, h->combined, h->logits_ws, h->drop_ws};
+    drop_graphs(h);
+    void* ps[] = {h->tok_a, h->tok_b, h->pred_buf, h->combined, h->logits_ws, h->drop_ws, h->labels_ws};
+    h->labels_ws = nullptr;
     for (void* p : ps) if (p) cudaFree(p);
     h->tok_a = h->tok_b = h->pred_buf = h->combined = nullptr; h->logits_ws = nullptr; h->drop_ws = nullptr; h->cap_sample_B = 0; h->drop_layout_B = 0;
 }
@@ -333,6 +348,9 @@ extern "C" void mb_destroy(mb_handle* h) {
     for (int m = 0; m < 2; ++m) for (auto& kv : h->staged[m]) cudaFree(kv.second.ptr);
     for (void* p : h->allocs) cudaFree(p);
     free_ws(h); free_sample_ws(h); free_dec_ws(h);
+    if (h->gstream) cudaStreamDestroy(h->gstream);
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->ev_out) cudaEventDestroy(h->ev_out);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
 }
@@ -1105,6 +1123,7 @@ static int ensure_sample_ws(mb_handle* h, int B) {
     MB_TRY(dev_alloc(h, &h->combined, (size_t)B * h->cfg.seq_len, false));
     MB_TRY(dev_alloc(h, &h->logits_ws, (size_t)2 * B * slots * h->V, false));
     MB_TRY(dev_alloc(h, &h->drop_ws, (size_t)2 * B, false));
+    MB_TRY(dev_alloc(h, &h->labels_ws, (size_t)B, false));
     CU_TRY(cudaMemset(h->drop_ws, 0, B));
     CU_TRY(cudaMemset(h->drop_ws + B, 1, B));
     h->cap_sample_B = B;
@@ -1112,13 +1131,61 @@ static int ensure_sample_ws(mb_handle* h, int B) {
     return 0;
 }
 
+// One generator forward replayed from a CUDA graph (captured on first use for this sequence count and token buffer).
+static int forward_graph(mb_handle* h, const int64_t* tokens, int B, int n_seq, cudaStream_t st) {
+    for (auto& g : h->fwd_graphs)
+        if (g.B == B && g.n_seq == n_seq && g.tokens == tokens) {
+            CU_TRY(cudaGraphLaunch(g.exec, st));
+            h->launches += g.nodes;
+            return 0;
+        }
+    MB_TRY(ensure_ws(h, n_seq));                       // allocations are not capturable: size the workspace first
+    const int64_t before = h->launches;
+    cudaGraph_t graph = nullptr;
+    CU_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = forward_impl(h, tokens, B, h->labels_ws, B, h->drop_ws, n_seq, h->logits_ws, st);
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    const int64_t nodes = h->launches - before;
+    h->launches = before;                              // nothing ran yet: launches are counted per replay
+    if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return fail(MB_ERR_CUDA, "stream capture of the generator forward failed: %s", cudaGetErrorString(ce));
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) return fail(MB_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+    if (h->fwd_graphs.size() >= 32) drop_graphs(h);    // a caller cycling through many batch sizes: start over
+    h->fwd_graphs.push_back({exec, B, n_seq, tokens, nodes});
+    CU_TRY(cudaGraphLaunch(exec, st));
+    h->launches += nodes;
+    return 0;
+}
+
+// batches up to this size replay captured forwards (MASKBIT_B200_GRAPH_MAX_BATCH overrides; 0 disables)
+static int graph_max_batch() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MASKBIT_B200_GRAPH_MAX_BATCH"); v = e ? atoi(e) : 16; }
+    return v;
+}
+
 extern "C" int mb_sample(mb_handle* h, const mb_sample_args* a, mb_stream stream) {
     if (!h || !a || !a->labels || a->B <= 0 || a->num_steps <= 0 || !a->scale || !a->temperature || !a->one_minus_progress || !a->mask_len)
         return fail(MB_ERR_INVALID, "mb_sample: bad argument");
-    cudaStream_t st = (cudaStream_t)stream;
+    cudaStream_t caller = (cudaStream_t)stream, st = caller;
     const mb_config& c = h->cfg;
     const int B = a->B;
     MB_TRY(ensure_sample_ws(h, B));
+    const bool use_graph = B <= graph_max_batch() && !h->profiling;
+    if (use_graph) {
+        if (!h->gstream) {
+            CU_TRY(cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking));
+            CU_TRY(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+        }
+        CU_TRY(cudaEventRecord(h->ev_in, caller));     // everything the caller enqueued so far (labels, noise) precedes the loop
+        st = h->gstream;
+        CU_TRY(cudaStreamWaitEvent(st, h->ev_in, 0));
+        CU_TRY(cudaMemcpyAsync(h->labels_ws, a->labels, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    }
     if (B != h->drop_layout_B) {  // the conditional / unconditional drop flags sit at [0, B) / [B, 2B): rebuild when B changes
         CU_TRY(cudaMemsetAsync(h->drop_ws, 0, B, st));   // (comparing against the capacity here left a smaller call's layout behind)
         CU_TRY(cudaMemsetAsync(h->drop_ws + B, 1, B, st));
@@ -1133,7 +1200,8 @@ extern "C" int mb_sample(mb_handle* h, const mb_sample_args* a, mb_stream stream
     for (int i = 0; i < a->num_steps; ++i) {
         const bool guided = a->use_guidance && !(a->skip_zero_scale_uncond && a->scale[i] == 0.0f);
         const int n_seq = guided ? 2 * B : B;
-        MB_TRY(forward_impl(h, cur, B, a->labels, B, h->drop_ws, n_seq, h->logits_ws, st));
+        if (use_graph) MB_TRY(forward_graph(h, cur, B, n_seq, st));
+        else MB_TRY(forward_impl(h, cur, B, a->labels, B, h->drop_ws, n_seq, h->logits_ws, st));
         mb_select_args s;
         s.logits_c = h->logits_ws;
         s.logits_u = guided ? h->logits_ws + (size_t)B * slots * h->V : nullptr;
@@ -1153,8 +1221,12 @@ extern "C" int mb_sample(mb_handle* h, const mb_sample_args* a, mb_stream stream
     // sampling.py:133-135: the LAST step's predicted tokens (all positions filled) are decoded
     if (a->images || a->final_tokens) {
         int64_t* comb = a->final_tokens ? a->final_tokens : h->combined;
-        MB_TRY(mb_combine_tokens(h, last_pred, B, comb, stream));
+        MB_TRY(mb_combine_tokens(h, last_pred, B, comb, (mb_stream)st));
         if (a->images) MB_TRY(decode_impl(h, comb, B, a->images, st));
+    }
+    if (use_graph) {                                   // the caller's stream continues after the loop
+        CU_TRY(cudaEventRecord(h->ev_out, st));
+        CU_TRY(cudaStreamWaitEvent(caller, h->ev_out, 0));
     }
     return 0;
 }
