@@ -53,6 +53,24 @@ def measured_peaks():
     return dict(bf16_sustained=1400.0, bf16_burst=1590.0, hbm=6650.0, source="fallback")
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Keep the process's stdout to the ONE JSON line the driver parses: everything else written to fd 1 -- NCCL's version
+    banner (printed by the library itself on init), stray prints of imported packages -- is sent to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    print(json.dumps(line), file=out, flush=True)
+
+
 def ncu_traffic(kind):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel class, from the committed `ncu --set full` capture
     (profiles/ncu_traffic.json, written by profiles/summarize.py traffic); None when no capture is committed."""
@@ -177,7 +195,7 @@ def run_reference(args):
             "config": workload_config(args),
             "cpu_baseline": {"value": v, "unit": "images/s", "cores": threads, "kind": "port", "sample": last["sample"]},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args):
@@ -209,9 +227,6 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL prints its version banner (NCCL_DEBUG=VERSION on the GPU boxes) to stdout by default: keep stdout to the one
-        # JSON line the driver parses
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = load_config(f"maskbit_generator_{args.bits}bit")
@@ -324,7 +339,7 @@ def run_b200(args):
             threads = os.cpu_count() or 1
             r = cpu_reference_sample(args.bits, args.cpu_batch, args.cpu_steps, T, threads)
             line["cpu_baseline"] = {"value": r["images_per_s"], "unit": "images/s", "cores": threads, "kind": "port", "sample": r["sample"]}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -392,7 +407,7 @@ def run_tokenizer(args):
                          "traffic": None, "peak_source": f"{peaks['source']} bf16_tflops_sustained", "launches": conv_n,
                          "note": "algorithmic (single-pass) conv FLOPs; the tensor pipe executes 3x that"},
             "kernel_time_share": {k: round(v[0] / gpu_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -415,6 +430,7 @@ def main():
     ap.add_argument("--no-library-ref", action="store_true", help="skip the 2 s cuBLASLt same-shape yardstick loop")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e pass (profiling runs under ncu only)")
     args = ap.parse_args()
+    claim_stdout()
     if args.batch is None:
         args.batch = 512 if args.workload == "tokenizer" else 256
     if args.workload == "tokenizer" and args.impl != "reference":
