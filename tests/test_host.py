@@ -153,3 +153,14 @@ def test_eval_driver_label_schedule():
     assert lab.dtype == torch.int64 and lab.shape == (2500,)
     assert sorted(lab[:1000].tolist()) == list(range(1000)) and torch.equal(lab[:1000], lab[1000:2000]) and torch.equal(lab[:500], lab[2000:])
     assert torch.equal(lab, label_schedule(2500, label_seed=5)) and not torch.equal(lab, label_schedule(2500, label_seed=6))
+
+
+def test_bench_flop_accounting_matches_survey():
+    """bench.py counts the algorithmic FLOPs SURVEY.md 8(d) states (2*MAC, CFG on every step, all 257 rows through the head)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.f_fwd(12) == 162_328_313_856 and bench.f_fwd(14) == 162_396_733_440
+    assert abs(bench.f_img(12, 64) - 20.964e12) < 0.001e12 and abs(bench.f_img(12, 8) - 2.783e12) < 0.001e12
+    assert abs(2 * 256 * bench.f_fwd(12) - 83.11e12) < 0.01e12          # transformer-step roofline numerator at B = 256
