@@ -40,7 +40,8 @@
 #define ATC_EV(role, ev, it) do {} while (0)
 #endif
 #ifndef ATC_PINGPONG
-#define ATC_PINGPONG 0      // named-barrier turn-taking of the two softmax warpgroups in pass 2: measured slower (0.417 vs 0.365 ms)
+#define ATC_PINGPONG 1      // named-barrier turn-taking of the two softmax warpgroups in pass 2 (first tried: slower, 0.417 vs 0.365 ms; with the
+                            // 3-input-max pass 1 it is 4 % faster, 0.374 vs 0.389 ms, and 1.3 % less energy per launch: tools/kpower.py)
 #endif
 
 namespace mb {
