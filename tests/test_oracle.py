@@ -57,6 +57,15 @@ def test_forward_matches_reference(bits, golden_dir, synthetic_checkpoints):
     assert (logits - ref).abs().max().item() <= 2e-5
 
 
+def test_forward_prenorm_matches_reference(golden_dir):
+    """The pre-norm branch of the oracle (bert.py:49-59,106-123,498-499) against the reference's own pre-norm logits."""
+    from maskbit_b200.weights import synthetic_lfq_bert_state_dict
+    g = np.load(os.path.join(golden_dir, "forward_prenorm_12bit.npz"))
+    sd = synthetic_lfq_bert_state_dict(seed=3, codebook_size=4096, depth=2, use_prenorm=True)
+    logits = O.lfq_bert_forward(sd, torch.from_numpy(g["tokens"].astype(np.int64)), torch.from_numpy(g["labels"]), torch.from_numpy(g["drop"]))
+    assert (logits - torch.from_numpy(g["logits"])).abs().max().item() <= 2e-5
+
+
 def test_decode_matches_reference(golden_dir, synthetic_checkpoints):
     g = np.load(os.path.join(golden_dir, "decode_12bit.npz"))
     _, dec_sd = synthetic_checkpoints(12)
