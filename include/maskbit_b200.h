@@ -142,6 +142,8 @@ typedef struct mb_sample_args {
     int64_t* trace;               /* device int64 [num_steps,B,n,splits] or NULL */
     int64_t* final_tokens;        /* device int64 [B,n] combined indices or NULL */
 } mb_sample_args;
+/* Batches of at most 16 images replay each forward as a CUDA graph on a stream owned by the handle, fenced by events to
+ * `stream` at entry and exit (ordering seen from `stream` is unchanged); MASKBIT_B200_GRAPH_MAX_BATCH=0 disables it. */
 int mb_sample(mb_handle* h, const mb_sample_args* a, mb_stream stream);
 
 /* Number of kernels the library has launched on this handle since creation (bench.py "gpu_launches"). */
