@@ -238,6 +238,7 @@ struct mb_handle {
     std::vector<FwdGraph> fwd_graphs;
     cudaStream_t gstream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    bool graphs_broken = false;          // a capture / instantiate failure: this handle stays on eager launches
     // decoder
     float *cin_w = nullptr, *cin_b = nullptr, *cout_w = nullptr, *cout_b = nullptr;
     int dec_c0 = 0, dec_cl = 0;
@@ -1200,8 +1201,15 @@ extern "C" int mb_sample(mb_handle* h, const mb_sample_args* a, mb_stream stream
     for (int i = 0; i < a->num_steps; ++i) {
         const bool guided = a->use_guidance && !(a->skip_zero_scale_uncond && a->scale[i] == 0.0f);
         const int n_seq = guided ? 2 * B : B;
-        if (use_graph) MB_TRY(forward_graph(h, cur, B, n_seq, st));
-        else MB_TRY(forward_impl(h, cur, B, a->labels, B, h->drop_ws, n_seq, h->logits_ws, st));
+        if (use_graph && !h->graphs_broken) {
+            if (forward_graph(h, cur, B, n_seq, st) != 0) {          // capture unsupported here: same work, launched eagerly
+                h->graphs_broken = true;
+                cudaGetLastError();
+                MB_TRY(forward_impl(h, cur, B, h->labels_ws, B, h->drop_ws, n_seq, h->logits_ws, st));
+            }
+        } else {
+            MB_TRY(forward_impl(h, cur, B, use_graph ? h->labels_ws : a->labels, B, h->drop_ws, n_seq, h->logits_ws, st));
+        }
         mb_select_args s;
         s.logits_c = h->logits_ws;
         s.logits_u = guided ? h->logits_ws + (size_t)B * slots * h->V : nullptr;
