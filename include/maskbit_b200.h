@@ -53,6 +53,7 @@ typedef struct mb_config {
     int dec_num_resolutions;   /* vq_model.num_resolutions (5) */
     int dec_num_res_blocks;    /* vq_model.num_res_blocks (2) */
     int num_channels;          /* vq_model.num_channels (3) */
+    int generator_cls;         /* mlm_model.model_cls: 0 "lfq_bert" (bert.py:344-508), 1 "bert" (embedding tables, bert.py:184-340) */
 } mb_config;
 
 int mb_create(const mb_config* cfg, mb_handle** out);

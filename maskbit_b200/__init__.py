@@ -4,7 +4,7 @@ Drop-in for the reference's `sample` / `LFQBert` / `ConvVQModel.decode_tokens` (
 layout); all compute runs in hand-written CUDA behind the C ABI of include/maskbit_b200.h.
 """
 from .config import load_config, sampler_kwargs, derive_sampling_config  # noqa: F401
-from .bert import LFQBert  # noqa: F401
+from .bert import Bert, LFQBert  # noqa: F401
 from .conv_vqgan import ConvVQModel  # noqa: F401
 from .sampling import sample  # noqa: F401
 from .factorization import combine_factorized_tokens, split_factorized_tokens  # noqa: F401
@@ -20,9 +20,9 @@ def build_models(config, device="cuda", generator_path=None, tokenizer_path=None
         tokenizer.load_pretrained(tokenizer_path)
     tokenizer.eval().requires_grad_(False)
     mlm = config.model.mlm_model
-    if mlm.model_cls != "lfq_bert":
-        raise NotImplementedError(f"model_cls {mlm.model_cls!r}: only 'lfq_bert' is implemented (every shipped config uses it)")
-    generator = LFQBert(
+    if mlm.model_cls not in ("lfq_bert", "bert"):      # train_maskbit.py:128-131 knows exactly these two
+        raise ValueError(f"model_cls {mlm.model_cls!r}: expected 'lfq_bert' or 'bert'")
+    generator = (LFQBert if mlm.model_cls == "lfq_bert" else Bert)(
         img_size=config.dataset.preprocessing.resolution, hidden_dim=mlm.hidden_dim,
         codebook_size=config.model.vq_model.codebook_size, codebook_splits=mlm.codebook_splits, depth=mlm.depth,
         heads=mlm.heads, mlp_dim=mlm.mlp_dim, dropout=mlm.dropout, use_prenorm=mlm.use_prenorm,

@@ -17,7 +17,7 @@ class MBConfig(ctypes.Structure):
                 ("token_bits", ctypes.c_int), ("codebook_splits", ctypes.c_int), ("nclass", ctypes.c_int),
                 ("seq_len", ctypes.c_int), ("use_prenorm", ctypes.c_int), ("dec_hidden_channels", ctypes.c_int),
                 ("dec_channel_mult", ctypes.c_int * 8), ("dec_num_resolutions", ctypes.c_int),
-                ("dec_num_res_blocks", ctypes.c_int), ("num_channels", ctypes.c_int)]
+                ("dec_num_res_blocks", ctypes.c_int), ("num_channels", ctypes.c_int), ("generator_cls", ctypes.c_int)]
 
 
 class MBSelectArgs(ctypes.Structure):

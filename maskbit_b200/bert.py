@@ -7,11 +7,12 @@ import torch
 
 from . import _lib
 from .base_model import EngineModel
-from .weights import lfq_bert_spec, synthetic_lfq_bert_state_dict
+from .weights import bert_spec, lfq_bert_spec, synthetic_bert_state_dict, synthetic_lfq_bert_state_dict
 
 
 class LFQBert(EngineModel):
     _model_id = _lib.MB_GENERATOR
+    _generator_cls = 0   # mb_config.generator_cls: 0 = LFQBert (bit-token input projection), 1 = Bert (embedding tables)
 
     def __init__(self, img_size=256, hidden_dim=768, codebook_size=1024, codebook_splits=1, depth=24, heads=8,
                  mlp_dim=3072, dropout=0.1, nclass=1000, input_stride: int = 16, use_prenorm: bool = False):
@@ -50,6 +51,7 @@ class LFQBert(EngineModel):
         c.hidden_dim, c.depth, c.heads, c.mlp_dim = self.hidden_dim, self.depth, self.heads, self.mlp_dim
         c.token_bits, c.codebook_splits, c.nclass, c.seq_len = self.bits, self.splits, self.nclass, self.seq_len
         c.use_prenorm = int(bool(self.use_prenorm))
+        c.generator_cls = self._generator_cls
         c.dec_hidden_channels = self._dec["hidden_channels"]
         for i, v in enumerate(self._dec["channel_mult"]):
             c.dec_channel_mult[i] = v
@@ -83,3 +85,17 @@ class LFQBert(EngineModel):
         return logits
 
     __call__ = forward
+
+
+class Bert(LFQBert):
+    """Mirror of modeling/bert.py:184-340, the embedding-table generator (``model_cls: "bert"``; no shipped config uses
+    it): same constructor, attributes and forward as LFQBert.  Tokens are looked up in one embedding table per split
+    (row ``effective_codebook_size`` = the mask token), and the logits of split i are the head output times the first
+    ``effective_codebook_size`` rows of that same table plus a per-position bias (bert.py:313-333)."""
+    _generator_cls = 1
+
+    def _expected_spec(self):
+        return [(n, s) for n, s, _ in bert_spec(**self._arch())]
+
+    def _default_state_dict(self):
+        return synthetic_bert_state_dict(seed=0, **self._arch())

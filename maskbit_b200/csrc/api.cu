@@ -215,6 +215,7 @@ struct mb_handle {
     // generator
     int bits = 0, eff_bits = 0, V = 0, S = 0;  // S = seq_len + 1
     float *w_in_t = nullptr, *b_in = nullptr, *class_emb = nullptr, *pos = nullptr;
+    float *tok_tables = nullptr, *pos_bias = nullptr;   // Bert (generator_cls 1): [splits][V+1][D] embedding tables, [splits][seq_len][V] logit bias
     LNW ln_first, ln_head, ln_after, ln_ident;   // ln_after / ln_ident: pre-norm trunk only
     std::vector<Layer> layers;
     Linear head, pred;
@@ -297,6 +298,7 @@ extern "C" int mb_create(const mb_config* cfg, mb_handle** out) {
     if (!cfg || !out) return fail(MB_ERR_INVALID, "mb_create: null argument");
     if (cfg->hidden_dim != 1024) return fail(MB_ERR_INVALID, "hidden_dim %d unsupported (row kernels are built for 1024)", cfg->hidden_dim);
     if (cfg->heads <= 0 || cfg->hidden_dim / cfg->heads != 64) return fail(MB_ERR_INVALID, "head dim must be 64");
+    if (cfg->generator_cls != 0 && cfg->generator_cls != 1) return fail(MB_ERR_INVALID, "generator_cls %d (0 lfq_bert, 1 bert)", cfg->generator_cls);
     if (cfg->codebook_splits < 1 || cfg->token_bits % cfg->codebook_splits) return fail(MB_ERR_INVALID, "token_bits must divide by codebook_splits");
     const int V = 1 << (cfg->token_bits / cfg->codebook_splits);
     if (V < 32 || V > 512) return fail(MB_ERR_INVALID, "per-group vocabulary %d unsupported (32..512)", V);
@@ -415,21 +417,25 @@ static int keep_f32(mb_handle* h, int model, const std::string& name, std::vecto
 }
 static int pick_bn(int N) { return N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 0)); }
 
-// Linear whose input is LayerNorm(y): fold gamma / beta of `ln` into the weights (see gemm_tcgen05.cuh)
-static int make_linear_lnin(mb_handle* h, const std::string& wname, const std::string& bname, int N, int K, const LNW& ln, Linear* L) {
-    DevTensor w, b;
-    MB_TRY(take(h, MB_GENERATOR, wname, {N, K}, &w));
-    MB_TRY(take(h, MB_GENERATOR, bname, {N}, &b));
+// Linear whose input is LayerNorm(y): fold gamma / beta of `ln` into the weights (see gemm_tcgen05.cuh).  w fp32 [N,K], b fp32 [N]
+static int make_linear_lnin_raw(mb_handle* h, const float* w, const float* b, int N, int K, const LNW& ln, Linear* L, const char* what) {
     L->N = N; L->K = K; L->BN = pick_bn(N);
-    if (!L->BN || K % 64) return fail(MB_ERR_INVALID, "linear %s: N=%d K=%d not tileable", wname.c_str(), N, K);
+    if (!L->BN || K % 64) return fail(MB_ERR_INVALID, "linear %s: N=%d K=%d not tileable", what, N, K);
     MB_TRY(dev_alloc(h, &L->w, (size_t)N * K));
     MB_TRY(dev_alloc(h, &L->b, (size_t)N));
     MB_TRY(dev_alloc(h, &L->v2, (size_t)N));
-    fold_ln_kernel<<<N, 256>>>(w.ptr, ln.g, ln.b, b.ptr, L->w, L->v2, L->b, K);
+    fold_ln_kernel<<<N, 256>>>(w, ln.g, ln.b, b, L->w, L->v2, L->b, K);
     CU_TRY(cudaGetLastError());
     MB_TRY(make_tmap_bf16(&L->tm, L->w, N, K, L->BN));
     if (L->BN == 256) MB_TRY(make_tmap_bf16(&L->tm_half, L->w, N, K, 128));
     CU_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+static int make_linear_lnin(mb_handle* h, const std::string& wname, const std::string& bname, int N, int K, const LNW& ln, Linear* L) {
+    DevTensor w, b;
+    MB_TRY(take(h, MB_GENERATOR, wname, {N, K}, &w));
+    MB_TRY(take(h, MB_GENERATOR, bname, {N}, &b));
+    MB_TRY(make_linear_lnin_raw(h, w.ptr, b.ptr, N, K, ln, L, wname.c_str()));
     cudaFree(w.ptr); cudaFree(b.ptr);
     h->staged[MB_GENERATOR].erase(wname); h->staged[MB_GENERATOR].erase(bname);
     return 0;
@@ -464,12 +470,29 @@ static int finalize_generator(mb_handle* h) {
     const mb_config& c = h->cfg;
     const int D = c.hidden_dim;
     DevTensor t;
-    MB_TRY(take(h, MB_GENERATOR, "input_proj.weight", {D, h->bits}, &t));
-    MB_TRY(dev_alloc(h, &h->w_in_t, (size_t)D * h->bits));
-    transpose_f32_kernel<<<(D * h->bits + 255) / 256, 256>>>(t.ptr, h->w_in_t, D, h->bits);
-    CU_TRY(cudaDeviceSynchronize());
-    cudaFree(t.ptr); h->staged[MB_GENERATOR].erase("input_proj.weight");
-    MB_TRY(keep_f32(h, MB_GENERATOR, "input_proj.bias", {D}, &h->b_in));
+    const bool bert = c.generator_cls == 1;
+    if (bert) {
+        // Bert (bert.py:225-227,255-257): per-split embedding tables [V+1, D] (row V = the mask token) and logit biases [seq_len, V]
+        const size_t rows = (size_t)h->V + 1;
+        MB_TRY(dev_alloc(h, &h->tok_tables, (size_t)c.codebook_splits * rows * D));
+        MB_TRY(dev_alloc(h, &h->pos_bias, (size_t)c.codebook_splits * c.seq_len * h->V));
+        for (int g = 0; g < c.codebook_splits; ++g) {
+            const std::string wn = "tok_emb_list." + std::to_string(g) + ".weight", bn = "bias." + std::to_string(g);
+            MB_TRY(take(h, MB_GENERATOR, wn, {(int64_t)rows, D}, &t));
+            CU_TRY(cudaMemcpy(h->tok_tables + (size_t)g * rows * D, t.ptr, rows * D * sizeof(float), cudaMemcpyDeviceToDevice));
+            cudaFree(t.ptr); h->staged[MB_GENERATOR].erase(wn);
+            MB_TRY(take(h, MB_GENERATOR, bn, {c.seq_len, h->V}, &t));
+            CU_TRY(cudaMemcpy(h->pos_bias + (size_t)g * c.seq_len * h->V, t.ptr, (size_t)c.seq_len * h->V * sizeof(float), cudaMemcpyDeviceToDevice));
+            cudaFree(t.ptr); h->staged[MB_GENERATOR].erase(bn);
+        }
+    } else {
+        MB_TRY(take(h, MB_GENERATOR, "input_proj.weight", {D, h->bits}, &t));
+        MB_TRY(dev_alloc(h, &h->w_in_t, (size_t)D * h->bits));
+        transpose_f32_kernel<<<(D * h->bits + 255) / 256, 256>>>(t.ptr, h->w_in_t, D, h->bits);
+        CU_TRY(cudaDeviceSynchronize());
+        cudaFree(t.ptr); h->staged[MB_GENERATOR].erase("input_proj.weight");
+        MB_TRY(keep_f32(h, MB_GENERATOR, "input_proj.bias", {D}, &h->b_in));
+    }
     MB_TRY(keep_f32(h, MB_GENERATOR, "class_emb.weight", {c.nclass + 1, D}, &h->class_emb));
     MB_TRY(keep_f32(h, MB_GENERATOR, "pos_emb", {1, h->S, D}, &h->pos));
     // every LayerNorm first: each one is folded into the Linears that consume its output
@@ -507,7 +530,23 @@ static int finalize_generator(mb_handle* h) {
     }
     const LNW& ln_last = pre ? h->ln_after : (c.depth > 0 ? h->layers[c.depth - 1].ln2 : h->ln_first);
     MB_TRY(make_linear_lnin(h, "last_layer.0.weight", "last_layer.0.bias", D, D, ln_last, &h->head));
-    MB_TRY(make_linear_lnin(h, "prediction_layer.weight", "prediction_layer.bias", c.codebook_splits * h->V, D, h->ln_head, &h->pred));
+    if (bert) {
+        // tied output projection (bert.py:332): rows [0, V) of every split's table, stacked split-major like prediction_layer's
+        // "(m c)" columns; the per-position bias is added after the GEMM
+        const int N = c.codebook_splits * h->V;
+        float *wp = nullptr, *zb = nullptr;
+        CU_TRY(cudaMalloc(&wp, (size_t)N * D * sizeof(float)));
+        CU_TRY(cudaMalloc(&zb, (size_t)N * sizeof(float)));
+        CU_TRY(cudaMemset(zb, 0, (size_t)N * sizeof(float)));
+        for (int g = 0; g < c.codebook_splits; ++g)
+            CU_TRY(cudaMemcpy(wp + (size_t)g * h->V * D, h->tok_tables + (size_t)g * (h->V + 1) * D, (size_t)h->V * D * sizeof(float),
+                              cudaMemcpyDeviceToDevice));
+        const int rc = make_linear_lnin_raw(h, wp, zb, N, D, h->ln_head, &h->pred, "tied token-embedding projection");
+        cudaFree(wp); cudaFree(zb);
+        MB_TRY(rc);
+    } else {
+        MB_TRY(make_linear_lnin(h, "prediction_layer.weight", "prediction_layer.bias", c.codebook_splits * h->V, D, h->ln_head, &h->pred));
+    }
     // buffers of the reference module that carry no information for this path
     auto it = h->staged[MB_GENERATOR].find("bits_to_indices");
     if (it != h->staged[MB_GENERATOR].end()) { cudaFree(it->second.ptr); h->staged[MB_GENERATOR].erase(it); }
@@ -821,7 +860,8 @@ static int forward_impl(mb_handle* h, const int64_t* tokens, int n_token_rows, c
         embed_kernel<D><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(tokens, n_token_rows, labels, n_label_rows, drop, n_seq, c.seq_len,
                                                                   c.codebook_splits, h->eff_bits, c.nclass, h->w_in_t, h->b_in,
                                                                   h->class_emb, h->pos, h->yA, h->stA, LN_PARTIALS,
-                                                                  c.use_prenorm ? h->ln_first.g : nullptr, c.use_prenorm ? h->ln_first.b : nullptr);
+                                                                  c.use_prenorm ? h->ln_first.g : nullptr, c.use_prenorm ? h->ln_first.b : nullptr,
+                                                                  h->tok_tables);
     }
     CU_TRY(cudaGetLastError()); h->launches++;
     // pre-norm: the residual epilogues add the stream as stored (no statistics -> identity LayerNorm)
@@ -840,6 +880,12 @@ static int forward_impl(mb_handle* h, const int64_t* tokens, int n_token_rows, c
     // head (bert.py:500-503): LN(gelu(W LN2(yA) + b)) -> prediction layer, class-token row dropped
     MB_TRY(run_linear(h, MB_PROF_GEMM_HEAD, h->tm_yA, h->head, M, EPI_LNIN_GELU_BF16_STATS, nullptr, h->stA, h->stB, h->yB, &h->tmo_yB, D, st));
     MB_TRY(run_linear(h, MB_PROF_GEMM_HEAD, h->tm_yB, h->pred, M, EPI_LNIN_F32_SEQ, nullptr, h->stB, nullptr, logits, nullptr, h->pred.N, st, h->S, c.seq_len));
+    if (h->pos_bias) {   // Bert: + bias[split][position][v] (bert.py:333)
+        ProfScope prof(h, MB_PROF_GEMM_HEAD, st);
+        const long long total = (long long)n_seq * c.seq_len * h->pred.N;
+        add_pos_bias_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(logits, h->pos_bias, total, c.seq_len, c.codebook_splits, h->V);
+        CU_TRY(cudaGetLastError()); h->launches++;
+    }
     return 0;
 }
 

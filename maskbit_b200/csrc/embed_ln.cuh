@@ -22,6 +22,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 //          (drop == nullptr: every label dropped -- the reference's drop_label_mask=None quirk, bert.py:484)
 // w_in_t   fp32 [bits, D] = input_proj.weight transposed;  pos fp32 [seq_len+1, D];  class_emb fp32 [nclass+1, D]
 // y        bf16 [rows, D] pre-LayerNorm sum;  stats float2 [rows][n_partials]: slot 0 = (sum, sumsq) of the stored row, rest 0
+// tok_tables  nullptr for LFQBert.  Bert (embedding-table generator, bert.py:313-315): fp32 [splits][V+1][D], the row of token t of
+//          split g is added (t = V is the mask token's own learned row); w_in_t / b_in are unused.
 // ln_g/ln_b  nullptr for the post-norm trunk.  Pre-norm trunk (use_prenorm, bert.py:496 with :106-123): the residual stream carries
 //          first_layer's LayerNorm OUTPUT, so it is applied here (fp32 statistics of the fp32 row, eps 1e-12) before the store.
 template <int D>
@@ -30,7 +32,8 @@ embed_kernel(const int64_t* __restrict__ tokens, int n_token_rows, const int64_t
              const uint8_t* __restrict__ drop, int n_seq, int seq_len, int splits, int eff_bits, int nclass,
              const float* __restrict__ w_in_t, const float* __restrict__ b_in, const float* __restrict__ class_emb,
              const float* __restrict__ pos, __nv_bfloat16* __restrict__ y, float2* __restrict__ stats, int n_partials,
-             const float* __restrict__ ln_g = nullptr, const float* __restrict__ ln_b = nullptr) {
+             const float* __restrict__ ln_g = nullptr, const float* __restrict__ ln_b = nullptr,
+             const float* __restrict__ tok_tables = nullptr) {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long rows = (long long)n_seq * (seq_len + 1);
@@ -38,7 +41,22 @@ embed_kernel(const int64_t* __restrict__ tokens, int n_token_rows, const int64_t
     const int n = (int)(row / (seq_len + 1)), s = (int)(row - (long long)n * (seq_len + 1));
     float x[D / 32];   // row elements e = 4*(lane + 32*j) + i  (j = 0..D/128-1, i = 0..3)
     const float* prow = pos + (size_t)s * D;
-    if (s < seq_len) {
+    if (s < seq_len && tok_tables != nullptr) {
+        const int64_t* trow = tokens + ((size_t)(n % n_token_rows) * seq_len + s) * splits;
+        const int64_t rows_per_table = ((int64_t)1 << eff_bits) + 1;
+#pragma unroll
+        for (int i = 0; i < D / 32; ++i) x[i] = 0.f;
+        for (int g = 0; g < splits; ++g) {
+            int64_t tok = trow[g];
+            tok = tok < 0 ? 0 : (tok >= rows_per_table ? rows_per_table - 1 : tok);     // stay inside the table
+            const float* w = tok_tables + ((size_t)g * rows_per_table + tok) * D;
+#pragma unroll
+            for (int j = 0; j < D / 128; ++j) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(w + 4 * (lane + 32 * j)));
+                x[4 * j] += v.x; x[4 * j + 1] += v.y; x[4 * j + 2] += v.z; x[4 * j + 3] += v.w;
+            }
+        }
+    } else if (s < seq_len) {
 #pragma unroll
         for (int j = 0; j < D / 128; ++j) {
             const float4 v = __ldg(reinterpret_cast<const float4*>(b_in + 4 * (lane + 32 * j)));
@@ -109,6 +127,16 @@ embed_kernel(const int64_t* __restrict__ tokens, int n_token_rows, const int64_t
     }
     sum = warp_sum(sum); sq = warp_sum(sq);
     if (lane < n_partials) stats[(size_t)row * n_partials + lane] = lane == 0 ? make_float2(sum, sq) : make_float2(0.f, 0.f);
+}
+
+// Bert's per-position logit bias (bert.py:333): logits fp32 [n_seq, seq_len, splits, V] += bias[splits][seq_len][V]
+__global__ void add_pos_bias_kernel(float* __restrict__ logits, const float* __restrict__ bias, long long total, int seq_len, int splits, int V) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int v = (int)(i % V);
+    const int g = (int)((i / V) % splits);
+    const int s = (int)((i / ((long long)V * splits)) % seq_len);
+    logits[i] += __ldg(bias + ((size_t)g * seq_len + s) * V + v);
 }
 
 }  // namespace mb

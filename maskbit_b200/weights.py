@@ -75,6 +75,30 @@ def lfq_bert_spec(hidden_dim=1024, codebook_size=4096, codebook_splits=2, depth=
     return spec
 
 
+def bert_spec(hidden_dim=1024, codebook_size=4096, codebook_splits=2, depth=24, mlp_dim=4096, nclass=1000, seq_len=256,
+              use_prenorm=False):
+    """(name, shape, kind) for every tensor of the embedding-table generator ``Bert`` (bert.py:184-258): the transformer
+    and last_layer of LFQBert, per-split token embeddings (row V = the mask token) that are also the output projection,
+    and a per-position logit bias per split."""
+    bits = int(math.log2(codebook_size))
+    v = 2 ** (bits // codebook_splits)
+    D = hidden_dim
+    trunk = [e for e in lfq_bert_spec(hidden_dim, codebook_size, codebook_splits, depth, mlp_dim, nclass, seq_len, use_prenorm)
+             if e[0].startswith(("first_layer", "transformer", "norm_after_transformer", "last_layer"))]
+    spec = [("pos_emb", (1, seq_len + 1, D), "w"), ("class_emb.weight", (nclass + 1, D), "w")]
+    spec += [(f"tok_emb_list.{i}.weight", (v + 1, D), "w") for i in range(codebook_splits)]
+    spec += trunk
+    spec += [(f"bias.{i}", (seq_len, v), "b") for i in range(codebook_splits)]
+    return spec
+
+
+def synthetic_bert_state_dict(seed=0, weight_std=0.02, **arch):
+    sd = OrderedDict()
+    for name, shape, kind in bert_spec(**arch):
+        sd[name] = _t(name, shape, {"w": weight_std, "b": 0.02, "g": 0.1}[kind], seed, mean=1.0 if kind == "g" else 0.0)
+    return sd
+
+
 def synthetic_lfq_bert_state_dict(seed=0, weight_std=0.02, **arch):
     """Synthetic LFQBert checkpoint.  weight_std 0.02 = the reference's trunc-normal sigma (bert.py:427-432)."""
     sd = OrderedDict()

@@ -93,26 +93,10 @@ def mha(x, w_in, b_in, w_out, b_out, heads):
     return o @ w_out.t() + b_out
 
 
-def lfq_bert_forward(sd, img_tokens, class_labels, drop_label_mask, *, heads=16, splits=2, nclass=1000,
-                     return_hidden=False):
-    """LFQBert.forward (bert.py:456-508), post-norm, or pre-norm when the checkpoint carries ``norm_after_transformer``
-    (use_prenorm=True: bert.py:49-59,106-123,407-408,498-499).  Returns fp32 logits [N, seq_len, splits, V].
-
-    Does not mutate class_labels (the reference mutates a view in place, bert.py:484; harmless in sample()).
-    drop_label_mask=None reproduces the reference quirk ``cls_token[None] = 1000`` (drops every label).
-    """
+def _trunk_and_head(sd, x, heads):
+    """first_layer -> TransformerEncoder (post- or pre-norm) -> [norm_after_transformer] -> last_layer, shared by LFQBert
+    (bert.py:496-500) and Bert (bert.py:324-328).  Returns (head output, per-layer hidden states)."""
     prenorm = "norm_after_transformer.weight" in sd
-    bits = sd["input_proj.weight"].shape[1]
-    n, seq_len, _ = img_tokens.shape
-    x_bits = preprocess_tokens(img_tokens, bits, splits)
-    cls = class_labels.clone().view(n)
-    if drop_label_mask is None:
-        cls[:] = nclass
-    else:
-        cls[drop_label_mask] = nclass
-    cls_emb = sd["class_emb.weight"][cls][:, None, :]
-    proj = x_bits @ sd["input_proj.weight"].t() + sd["input_proj.bias"]
-    x = torch.cat([proj, cls_emb], dim=1) + sd["pos_emb"]
     x = layer_norm(x, sd["first_layer.0.weight"], sd["first_layer.0.bias"])
     hidden = [x]
     depth = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("transformer.layers."))
@@ -138,12 +122,60 @@ def lfq_bert_forward(sd, img_tokens, class_labels, drop_label_mask, *, heads=16,
         x = layer_norm(x, sd["norm_after_transformer.weight"], sd["norm_after_transformer.bias"])   # bert.py:498-499
     y = gelu_erf(x @ sd["last_layer.0.weight"].t() + sd["last_layer.0.bias"])
     y = layer_norm(y, sd["last_layer.2.weight"], sd["last_layer.2.bias"])                  # bert.py:500
+    return y, hidden
+
+
+def lfq_bert_forward(sd, img_tokens, class_labels, drop_label_mask, *, heads=16, splits=2, nclass=1000,
+                     return_hidden=False):
+    """LFQBert.forward (bert.py:456-508), post-norm, or pre-norm when the checkpoint carries ``norm_after_transformer``
+    (use_prenorm=True: bert.py:49-59,106-123,407-408,498-499).  Returns fp32 logits [N, seq_len, splits, V].
+
+    Does not mutate class_labels (the reference mutates a view in place, bert.py:484; harmless in sample()).
+    drop_label_mask=None reproduces the reference quirk ``cls_token[None] = 1000`` (drops every label).
+    """
+    bits = sd["input_proj.weight"].shape[1]
+    n, seq_len, _ = img_tokens.shape
+    x_bits = preprocess_tokens(img_tokens, bits, splits)
+    cls = class_labels.clone().view(n)
+    if drop_label_mask is None:
+        cls[:] = nclass
+    else:
+        cls[drop_label_mask] = nclass
+    cls_emb = sd["class_emb.weight"][cls][:, None, :]
+    proj = x_bits @ sd["input_proj.weight"].t() + sd["input_proj.bias"]
+    x = torch.cat([proj, cls_emb], dim=1) + sd["pos_emb"]
+    y, hidden = _trunk_and_head(sd, x, heads)
     logits = y @ sd["prediction_layer.weight"].t() + sd["prediction_layer.bias"]
     v = logits.shape[-1] // splits
     logits = logits.view(n, seq_len + 1, splits, v)[:, :seq_len]                            # bert.py:502-503
     if return_hidden:
         return logits, hidden
     return logits
+
+
+def bert_forward(sd, img_tokens, class_labels, drop_label_mask, *, heads=16, nclass=1000):
+    """Bert.forward (bert.py:283-340), the embedding-table generator: token embeddings summed over the splits (row V of
+    each table = the mask token), the shared trunk, and per split ``x @ tok_emb[i][:V].T + bias[i]`` on the first seq_len
+    positions.  Returns fp32 logits [N, seq_len, splits, V]."""
+    splits = sum(1 for k in sd if k.startswith("tok_emb_list."))
+    n, seq_len, _ = img_tokens.shape
+    cls = class_labels.clone().view(n)
+    if drop_label_mask is None:
+        cls[:] = nclass
+    else:
+        cls[drop_label_mask] = nclass
+    cls_emb = sd["class_emb.weight"][cls][:, None, :]
+    tok = sd["tok_emb_list.0.weight"][img_tokens[..., 0]]
+    for i in range(1, splits):
+        tok = tok + sd[f"tok_emb_list.{i}.weight"][img_tokens[..., i]]                  # bert.py:313-315
+    x = torch.cat([tok, cls_emb], dim=1) + sd["pos_emb"]
+    y, _ = _trunk_and_head(sd, x, heads)
+    logits = []
+    for i in range(splits):
+        w = sd[f"tok_emb_list.{i}.weight"]
+        v = w.shape[0] - 1
+        logits.append((y @ w[:v].t())[:, :seq_len] + sd[f"bias.{i}"])                    # bert.py:331-333
+    return torch.stack(logits, dim=2)
 
 
 # ----------------------------------------------------------------------------------------------

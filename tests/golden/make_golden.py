@@ -13,6 +13,7 @@ Fixtures written (all small enough to commit):
   sample_12bit.npz    BASELINE config #1: sample() B=4, 8 steps, CFG cosine: per-step tokens + pixels
   forward_prenorm_12bit.npz  LFQBert(use_prenorm=True, depth=2).forward, 2 sequences (no shipped config uses pre-norm; the
                       branch is bert.py:49-59,106-123,498-499)
+  forward_bert_12bit.npz  Bert(depth=2).forward (embedding-table generator, bert.py:184-340), 2 sequences
   decode_12bit.npz    ConvVQModel.decode_tokens on random tokens, B=2
   encode_12bit.npz    ConvVQModel.forward (encode -> LFQ -> decode) on seeded images, B=2: latents z, indices, reconstruction
 """
@@ -29,12 +30,12 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, REF)
 sys.path.insert(0, ROOT)
 
-from modeling.bert import LFQBert  # noqa: E402  (reference)
+from modeling.bert import Bert, LFQBert  # noqa: E402  (reference)
 from modeling.conv_vqgan import ConvVQModel  # noqa: E402  (reference)
 from modeling.modules import sample as ref_sample  # noqa: E402  (reference)
 
 from maskbit_b200.config import load_config, sampler_kwargs  # noqa: E402
-from maskbit_b200.weights import synthetic_conv_vq_state_dict, synthetic_lfq_bert_state_dict  # noqa: E402
+from maskbit_b200.weights import synthetic_bert_state_dict, synthetic_conv_vq_state_dict, synthetic_lfq_bert_state_dict  # noqa: E402
 
 
 def build_reference(bits):
@@ -81,6 +82,15 @@ def golden_forward_prenorm(path):
     gen = LFQBert(img_size=256, hidden_dim=1024, codebook_size=4096, codebook_splits=2, depth=2, heads=16, mlp_dim=4096,
                   dropout=0.1, use_prenorm=True, input_stride=16)
     gen.load_state_dict(synthetic_lfq_bert_state_dict(seed=3, codebook_size=4096, depth=2, use_prenorm=True), strict=True)
+    gen.eval().requires_grad_(False)
+    golden_forward(gen, 12, 2, path)
+
+
+def golden_forward_bert(path):
+    """Embedding-table generator on a 2-layer model of the shipped width (hidden 1024, 16 heads, MLP 4096, 4096 codes in 2 splits)."""
+    gen = Bert(img_size=256, hidden_dim=1024, codebook_size=4096, codebook_splits=2, depth=2, heads=16, mlp_dim=4096,
+               dropout=0.1, use_prenorm=False, input_stride=16)
+    gen.load_state_dict(synthetic_bert_state_dict(seed=5, codebook_size=4096, depth=2), strict=True)
     gen.eval().requires_grad_(False)
     golden_forward(gen, 12, 2, path)
 
@@ -149,6 +159,7 @@ def main():
     cfg, kw, vq, gen = build_reference(12)
     golden_forward(gen, 12, 4, os.path.join(HERE, "forward_12bit.npz"))
     golden_forward_prenorm(os.path.join(HERE, "forward_prenorm_12bit.npz"))
+    golden_forward_bert(os.path.join(HERE, "forward_bert_12bit.npz"))
     golden_decode(vq, 12, os.path.join(HERE, "decode_12bit.npz"))
     golden_encode(vq, os.path.join(HERE, "encode_12bit.npz"))
     golden_sample(kw, vq, gen, 2, 4, os.path.join(HERE, "select_12bit.npz"), with_logits=True)

@@ -128,6 +128,26 @@ def test_forward_prenorm_matches_reference_golden(golden_dir):
         post.load_state_dict(sd, strict=True)          # the post-norm model has no norm_after_transformer
 
 
+def test_forward_bert_matches_reference_golden(golden_dir):
+    """Bert, the embedding-table generator (bert.py:184-340; model_cls "bert"): token-embedding gather, the shared trunk, the tied
+    output projection and the per-position bias, against the reference's own logits; then a short guided sample() through it."""
+    from maskbit_b200 import Bert
+    from maskbit_b200.weights import synthetic_bert_state_dict
+    d = np.load(os.path.join(golden_dir, "forward_bert_12bit.npz"))
+    gen = Bert(img_size=256, hidden_dim=1024, codebook_size=4096, codebook_splits=2, depth=2, heads=16, mlp_dim=4096,
+               dropout=0.1, use_prenorm=False, input_stride=16)
+    gen.load_state_dict(synthetic_bert_state_dict(seed=5, codebook_size=4096, depth=2), strict=True)
+    gen = gen.to("cuda")
+    tok = torch.from_numpy(d["tokens"].astype(np.int64))
+    assert int(tok.max()) == gen.mask_token                        # the fixture exercises the mask token's own embedding row
+    logits = gen(tok.cuda(), torch.from_numpy(d["labels"]).cuda(), torch.from_numpy(d["drop"]).cuda()).cpu()
+    diff = (logits - torch.from_numpy(d["logits"])).abs()
+    assert diff.max().item() <= LOGIT_MAX_ABS and diff.mean().item() <= LOGIT_MEAN_ABS, (diff.max().item(), diff.mean().item())
+    _, kw, tokenizer, _ = models(12)
+    img, trace = sample(gen, tokenizer, num_samples=2, labels=torch.tensor([1, 7]), noise="device", seed=3, **dict(kw, num_steps=3))
+    assert img.shape == (2, 3, 256, 256) and torch.isfinite(img).all() and all(int(t.max()) < 64 and int(t.min()) >= 0 for t in trace)
+
+
 def test_forward_drop_none_and_batch_invariance(golden_dir):
     """drop_label_mask=None drops every label (the reference quirk `cls_token[None] = 1000`, bert.py:482-484), and a
     sequence's logits do not depend on what else is in the batch (bit-exact: tiles never mix sequences' rows)."""

@@ -66,6 +66,15 @@ def test_forward_prenorm_matches_reference(golden_dir):
     assert (logits - torch.from_numpy(g["logits"])).abs().max().item() <= 2e-5
 
 
+def test_forward_bert_matches_reference(golden_dir):
+    """The embedding-table generator (bert.py:184-340) restated in the oracle against the reference's own logits."""
+    from maskbit_b200.weights import synthetic_bert_state_dict
+    g = np.load(os.path.join(golden_dir, "forward_bert_12bit.npz"))
+    sd = synthetic_bert_state_dict(seed=5, codebook_size=4096, depth=2)
+    logits = O.bert_forward(sd, torch.from_numpy(g["tokens"].astype(np.int64)), torch.from_numpy(g["labels"]), torch.from_numpy(g["drop"]))
+    assert (logits - torch.from_numpy(g["logits"])).abs().max().item() <= 2e-5
+
+
 def test_decode_matches_reference(golden_dir, synthetic_checkpoints):
     g = np.load(os.path.join(golden_dir, "decode_12bit.npz"))
     _, dec_sd = synthetic_checkpoints(12)
