@@ -54,6 +54,8 @@ typedef struct mb_config {
     int dec_num_res_blocks;    /* vq_model.num_res_blocks (2) */
     int num_channels;          /* vq_model.num_channels (3) */
     int generator_cls;         /* mlm_model.model_cls: 0 "lfq_bert" (bert.py:344-508), 1 "bert" (embedding tables, bert.py:184-340) */
+    int enc_num_res_blocks;    /* vq_model.num_res_blocks for the ENCODER (autoencoder.py:230-286); dec_num_res_blocks carries the
+                                  decoder's num_res_blocks_decoder override (autoencoder.py:371).  0 = same as the decoder */
 } mb_config;
 
 int mb_create(const mb_config* cfg, mb_handle** out);
@@ -183,6 +185,9 @@ int mb_test_gemm(const uint16_t* A, const uint16_t* W, const float* bias, const 
 int mb_test_gemm_ex(const uint16_t* A, const uint16_t* W, const float* bias, const float* vec2, const uint16_t* residual,
                     const float* stats_in, float* stats_out, void* out, int M, int N, int K, int epi, int seq_in, int seq_out,
                     float inv_d, float eps, mb_stream stream);
+/* The production-mode (device Philox) noise transforms of the select kernel applied to raw 32-bit draws r[n]:
+ * u = uniform in (0,1), q = Exp(1) = -log u, g = Gumbel(0,1) = -log(-log u).  All three finite for every r. */
+int mb_test_noise_transform(const uint32_t* r, float* u, float* q, float* g, int n, mb_stream stream);
 /* qkv bf16 [n_seq*S, 3*D] -> out bf16 [n_seq*S, D] */
 int mb_test_attention(const uint16_t* qkv, uint16_t* out, int n_seq, int S, int D, int H, mb_stream stream);
 /* builds with -DATC_TRACE=1 only: device buffer int64 [8 roles][8 events][12 items] receiving block 0's clock64 stamps */

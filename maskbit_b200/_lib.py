@@ -17,7 +17,8 @@ class MBConfig(ctypes.Structure):
                 ("token_bits", ctypes.c_int), ("codebook_splits", ctypes.c_int), ("nclass", ctypes.c_int),
                 ("seq_len", ctypes.c_int), ("use_prenorm", ctypes.c_int), ("dec_hidden_channels", ctypes.c_int),
                 ("dec_channel_mult", ctypes.c_int * 8), ("dec_num_resolutions", ctypes.c_int),
-                ("dec_num_res_blocks", ctypes.c_int), ("num_channels", ctypes.c_int), ("generator_cls", ctypes.c_int)]
+                ("dec_num_res_blocks", ctypes.c_int), ("num_channels", ctypes.c_int), ("generator_cls", ctypes.c_int),
+                ("enc_num_res_blocks", ctypes.c_int)]
 
 
 class MBSelectArgs(ctypes.Structure):
@@ -61,6 +62,7 @@ SYMBOLS = {
     "mb_profile_read": (_I, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64), _I]),
     "mb_test_gemm": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "mb_test_attention": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "mb_test_noise_transform": (_I, [_P, _P, _P, _P, _I, _P]),
     "mb_test_attention_trace": (_I, [_P]),
     "mb_test_gemm_trace": (_I, [_P]),
     "mb_test_gemm_ex": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _P]),

@@ -5,7 +5,6 @@ same file layout (``pytorch_model.bin`` = torch.save(state_dict)), same ``rename
 loading, eval mode.  The weights themselves live inside libmaskbit_b200 (bf16 / split-bf16 packed); this class
 keeps the fp32 CPU state_dict only so that ``state_dict()`` / ``save_pretrained`` round-trip.
 """
-import copy
 import ctypes
 import os
 from collections import OrderedDict
@@ -84,29 +83,26 @@ class EngineModel:
             self._upload()
         return self
 
+    @staticmethod
+    def _checkpoint_file(path):
+        """A checkpoint file itself, or `pytorch_model.bin` inside a checkpoint directory (base_model.py:108-117)."""
+        candidate = os.path.join(path, "pytorch_model.bin") if os.path.isdir(path) else path
+        if not os.path.isfile(candidate):
+            raise ValueError(f"{candidate} does not exist")
+        return candidate
+
     def load_pretrained(self, pretrained_model_path, strict_loading=True, torch_dtype=None, rename_keys=None):
-        """base_model.py:87-142."""
-        if os.path.isfile(pretrained_model_path):
-            model_file = pretrained_model_path
-        elif os.path.isdir(pretrained_model_path):
-            pretrained_model_path = os.path.join(pretrained_model_path, "pytorch_model.bin")
-            if os.path.isfile(pretrained_model_path):
-                model_file = pretrained_model_path
-            else:
-                raise ValueError(f"{pretrained_model_path} does not exist")
-        else:
-            raise ValueError(f"{pretrained_model_path} does not exist")
-        checkpoint = torch.load(model_file, map_location="cpu")
-        new_checkpoint = copy.copy(checkpoint)
-        if rename_keys is not None:
-            for p_key in checkpoint:
-                for r_key in rename_keys:
-                    if p_key.startswith(r_key):
-                        new_checkpoint[p_key.replace(r_key, rename_keys[r_key])] = checkpoint[p_key]
-                        new_checkpoint.pop(p_key)
-                        break
-            checkpoint = new_checkpoint
-        self.load_state_dict(checkpoint, strict=strict_loading)
+        """Same contract as the reference's BaseModel.load_pretrained (base_model.py:87-142): load a state dict from a file or a
+        checkpoint directory, optionally rename keys (`rename_keys` maps an old key prefix to its replacement; the first matching
+        prefix wins and, like the reference's str.replace, every occurrence inside the key is replaced), load strictly unless told
+        otherwise, end in eval mode."""
+        loaded = torch.load(self._checkpoint_file(pretrained_model_path), map_location="cpu")
+
+        def renamed(key):
+            hit = next((old for old in (rename_keys or {}) if key.startswith(old)), None)
+            return key if hit is None else key.replace(hit, rename_keys[hit])
+
+        self.load_state_dict({renamed(k): v for k, v in loaded.items()}, strict=strict_loading)
         if torch_dtype is not None and not isinstance(torch_dtype, torch.dtype):
             raise ValueError(f"{torch_dtype} needs to be of type `torch.dtype`, e.g. `torch.float16`, but is {type(torch_dtype)}.")
         if torch_dtype not in (None, torch.float32):

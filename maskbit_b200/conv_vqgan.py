@@ -18,6 +18,9 @@ class ConvVQModel(EngineModel):
             raise NotImplementedError("legacy=True (ConvDecoderLegacy) is outside the MaskBit sampling path (eval_maskbit.py:26 uses legacy=False)")
         if config.quantizer_type != "lookup-free":
             raise NotImplementedError("only the lookup-free quantizer is on the MaskBit sampling path")
+        if not config.get("sample_with_conv", True):
+            raise NotImplementedError("sample_with_conv=False (pooling / plain interpolation stages, autoencoder.py:160-183,216-227) is not built: "
+                                      "every shipped tokenizer config uses strided / upsample convolutions")
         self.config = config
         self.finetune_decoder = finetune_decoder
         self.token_size = int(config.token_size)
@@ -26,7 +29,8 @@ class ConvVQModel(EngineModel):
         c = self.config
         return dict(token_size=self.token_size, num_channels=c.num_channels, hidden_channels=c.hidden_channels,
                     channel_mult=tuple(c.channel_mult), num_resolutions=c.num_resolutions,
-                    num_res_blocks=c.get("num_res_blocks_decoder", c.num_res_blocks))
+                    num_res_blocks=c.get("num_res_blocks_decoder", c.num_res_blocks),      # ConvDecoder (autoencoder.py:371)
+                    num_res_blocks_encoder=c.num_res_blocks)                               # ConvEncoder (autoencoder.py:245)
 
     def _expected_spec(self):
         return [(n, s) for n, s, _ in conv_vq_spec(**self._arch())]
@@ -45,6 +49,7 @@ class ConvVQModel(EngineModel):
         for i, v in enumerate(a["channel_mult"]):
             c.dec_channel_mult[i] = v
         c.dec_num_resolutions, c.dec_num_res_blocks, c.num_channels = a["num_resolutions"], a["num_res_blocks"], a["num_channels"]
+        c.enc_num_res_blocks = a["num_res_blocks_encoder"]
         return c
 
     @property

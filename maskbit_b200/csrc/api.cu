@@ -628,6 +628,7 @@ static int finalize_tokenizer(mb_handle* h) {
     // ---- encoder
     {
         const int c0 = hc;
+        const int enc_blocks = c.enc_num_res_blocks > 0 ? c.enc_num_res_blocks : c.dec_num_res_blocks;
         h->enc_c0 = c0;
         MB_TRY(take(h, MB_TOKENIZER, "encoder.conv_in.weight", {c0, 3, 3, 3}, &t));
         MB_TRY(dev_alloc(h, &h->enc_cin_w, (size_t)27 * c0));
@@ -640,15 +641,15 @@ static int finalize_tokenizer(mb_handle* h) {
             cin_l = hc * (lvl == 0 ? 1 : c.dec_channel_mult[lvl - 1]);
             cout_l = hc * c.dec_channel_mult[lvl];
             auto& stg = h->enc_down[lvl];
-            stg.blocks.resize(c.dec_num_res_blocks);
-            for (int r = 0; r < c.dec_num_res_blocks; ++r)
+            stg.blocks.resize(enc_blocks);
+            for (int r = 0; r < enc_blocks; ++r)
                 MB_TRY(make_block(h, "encoder.down." + std::to_string(lvl) + ".res_blocks." + std::to_string(r) + ".", r == 0 ? cin_l : cout_l, cout_l, &stg.blocks[r]));
             stg.has_down = lvl < nr - 1;
             if (stg.has_down) MB_TRY(make_conv(h, "encoder.down." + std::to_string(lvl) + ".down_conv", cout_l, cout_l, 3, true, &stg.down));
         }
         h->enc_cl = cout_l;
-        h->enc_mid.resize(c.dec_num_res_blocks);
-        for (int r = 0; r < c.dec_num_res_blocks; ++r)
+        h->enc_mid.resize(enc_blocks);
+        for (int r = 0; r < enc_blocks; ++r)
             MB_TRY(make_block(h, "encoder.mid.res_blocks." + std::to_string(r) + ".", cout_l, cout_l, &h->enc_mid[r]));
         MB_TRY(make_gn(h, "encoder.norm_out", cout_l, &h->enc_norm_out));
         DevTensor tw;
@@ -809,6 +810,7 @@ static int ensure_ws(mb_handle* h, int n_seq) {
     CU_TRY(cudaMemset(h->qkv, 0, rows * 3 * D * 2));
     CU_TRY(cudaMemset(h->att, 0, rows * D * 2));
     CU_TRY(cudaMemset(h->hmid, 0, rows * h->cfg.mlp_dim * 2));
+    CU_TRY(cudaDeviceSynchronize());   // (as in ensure_sample_ws: the consumers may run on non-blocking streams)
     MB_TRY(make_tmap_bf16(&h->tm_yA, h->yA, rows, D, 128));
     MB_TRY(make_tmap_bf16(&h->tm_yB, h->yB, rows, D, 128));
     MB_TRY(make_tmap_bf16(&h->tm_att, h->att, rows, D, 128));
@@ -1173,6 +1175,7 @@ static int ensure_sample_ws(mb_handle* h, int B) {
     MB_TRY(dev_alloc(h, &h->labels_ws, (size_t)B, false));
     CU_TRY(cudaMemset(h->drop_ws, 0, B));
     CU_TRY(cudaMemset(h->drop_ws + B, 1, B));
+    CU_TRY(cudaDeviceSynchronize());   // legacy-stream memsets are not ordered before work on non-blocking streams
     h->cap_sample_B = B;
     h->drop_layout_B = B;
     return 0;
@@ -1318,6 +1321,16 @@ extern "C" int mb_test_gemm_ex(const uint16_t* A, const uint16_t* W, const float
 extern "C" int mb_test_gemm(const uint16_t* A, const uint16_t* W, const float* bias, const uint16_t* residual, void* out, int M,
                             int N, int K, int epi, int seq_in, int seq_out, mb_stream stream) {
     return mb_test_gemm_ex(A, W, bias, nullptr, residual, nullptr, nullptr, out, M, N, K, epi, seq_in, seq_out, 0.f, 0.f, stream);
+}
+__global__ void noise_transform_kernel(const uint32_t* __restrict__ r, float* __restrict__ u, float* __restrict__ q, float* __restrict__ g, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { u[i] = u01_open(r[i]); q[i] = sel_exp1(r[i]); g[i] = sel_gumbel(r[i]); }
+}
+extern "C" int mb_test_noise_transform(const uint32_t* r, float* u, float* q, float* g, int n, mb_stream stream) {
+    if (!r || !u || !q || !g || n <= 0) return fail(MB_ERR_INVALID, "mb_test_noise_transform: bad argument");
+    noise_transform_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(r, u, q, g, n);
+    CU_TRY(cudaGetLastError());
+    return 0;
 }
 extern "C" int mb_test_attention(const uint16_t* qkv, uint16_t* out, int n_seq, int S, int D, int H, mb_stream stream) {
     MB_TRY(init_kernel_attrs());

@@ -6,17 +6,20 @@
 //               class-token rows (row 256 of Q, K, V) into a 2-stage shared-memory ring
 //   warps 1,2   MMA issuers (one thread each, one per 128-query tile t):
 //                   S_t = Q_t K^T            tcgen05.mma M128 N256 K16 x4, smem x smem
-//                   O_t = P_t V              A = P from TMEM, B = V MN-major from smem, 16 K-steps split over two
-//                                            accumulators (even / odd steps): dependent small MMAs are latency bound
-//   warp 3      the 257th row and column on warp-level mma.sync tiles:
-//                   s256[q] = Q[q] . K[256] for the 256 tile queries -> smem (the class-token KEY column)
-//                   the class-token QUERY row q = 256 against all 257 keys, softmax, P V -> global
+//                   O_t = P_t V              A = P from TMEM, B = V MN-major from smem, 16 K-steps into one accumulator
+//   warp 3      the class-token QUERY row q = 256: softmax over its 257 scores (256 of them computed by the softmax warps,
+//               below), then O = p V as 68 warp-level mma.sync tiles (A = V^T via ldmatrix.trans, B = p in column 0) -> global
 //               (also allocates TMEM, 512 columns)
-//   warps 4-11  softmax: warpgroup t owns query tile t, thread = one query row.  Pass 1 row max over S_t in TMEM,
+//   warps 4-11  softmax: warpgroup t owns query tile t, thread = one query row.  First the 257th row and column for the
+//               warp's own 32 rows / keys on mma.sync tiles (16 ldmatrix + 16 mma per warp, while the S MMAs run):
+//                   s256[r] = Q[r] . K[256]  (class-token KEY column, stays in a register of the row's thread)
+//                   scls[r] = Q[256] . K[r]  (class-token QUERY row) -> smem for warp 3
+//               (one warp doing all of this cost 10 k clk per item and set the kernel's pace: profiles/r02a_attn_trace.txt).
+//               Pass 1 row max over S_t in TMEM,
 //               pass 2 exp2 -> bf16 P written back over the S columns already consumed (FFMA2 + MUFU + F2FP + FADD2),
-//               epilogue (O_a + O_b + p256 V[256]) / l -> bf16 -> global.  The two warpgroups take turns in pass 2
+//               epilogue (O + p256 V[256]) / l -> bf16 -> global.  The two warpgroups take turns in pass 2
 //               (named-barrier ping-pong) so each has the MUFU pipe to itself while the other waits on its MMAs.
-// TMEM per query tile (256 columns): S fp32 [0,256) -> P packed bf16x2 [0,128), O_a [128,192), O_b [192,256).
+// TMEM per query tile (256 columns): S fp32 [0,256) -> P packed bf16x2 [0,128), O [128,192).
 // 257 = 2*128 + 1: tensor tiles cover the 256x256 block exactly; the odd row and column never touch a padded tcgen05 tile.
 //
 // Input  qkv  bf16 [rows, 3*D] through two TMA maps (box 64x256 and box 64x16); head h at columns h*64 of each third
@@ -50,8 +53,9 @@ constexpr int ATC_THREADS = 384;
 constexpr int ATC_TILE_BYTES = 256 * 128;             // 256 rows x 64 bf16
 constexpr int ATC_ROW_BYTES = 16 * 128;               // 16-row box holding the class-token row in its first 128 B
 constexpr int ATC_STAGE_BYTES = 3 * ATC_TILE_BYTES + 3 * ATC_ROW_BYTES;
-constexpr int ATC_S256_BYTES = 2 * 256 * 4;           // class-key scores of the 256 tile queries, per stage
-constexpr int ATC_SMEM_BYTES = 2 * ATC_STAGE_BYTES + ATC_S256_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int ATC_SCLS_BYTES = 2 * 256 * 4;           // class-query scores against the 256 tile keys, per stage
+constexpr int ATC_PCLS_BYTES = 576;                   // class-query probabilities, bf16 [272] (keys 257.. = 0)
+constexpr int ATC_SMEM_BYTES = 2 * ATC_STAGE_BYTES + ATC_SCLS_BYTES + ATC_PCLS_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 // D[tmem] (+)= A[tmem] * B[smem]
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -127,15 +131,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
     extern __shared__ uint8_t atc_smem_raw[];
     const uint32_t raw = smem_u32(atc_smem_raw);
     uint8_t* base = atc_smem_raw + ((1024u - (raw & 1023u)) & 1023u);
-    float* s256buf = reinterpret_cast<float*>(base + 2 * ATC_STAGE_BYTES);           // [2 stages][256 queries]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + 2 * ATC_STAGE_BYTES + ATC_S256_BYTES);
+    float* scls = reinterpret_cast<float*>(base + 2 * ATC_STAGE_BYTES);              // [2 stages][256 keys]
+    __nv_bfloat16* pcls = reinterpret_cast<__nv_bfloat16*>(base + 2 * ATC_STAGE_BYTES + ATC_SCLS_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + 2 * ATC_STAGE_BYTES + ATC_SCLS_BYTES + ATC_PCLS_BYTES);
     uint64_t* full = bars;           // [2] TMA landed
     uint64_t* empty = bars + 2;      // [2] stage consumed (2 MMA issuers' commits + 8 softmax warps + class warp)
     uint64_t* s_full = bars + 4;     // [2] S_t complete in TMEM
     uint64_t* p_full = bars + 6;     // [2] P_t written to TMEM (4 warps)
     uint64_t* o_full = bars + 8;     // [2] O_t complete
     uint64_t* t_free = bars + 10;    // [2] TMEM region t drained by the epilogue (4 warps)
-    uint64_t* cls_ready = bars + 12; // [2] s256buf[stage] written by the class warp
+    uint64_t* scls_ready = bars + 12;// [2] scls[stage] written by the 8 softmax warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -144,7 +149,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
         for (int s = 0; s < 2; ++s) {
             mbar_init(&full[s], 1); mbar_init(&empty[s], 11);
             mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 4); mbar_init(&o_full[s], 1); mbar_init(&t_free[s], 4);
-            mbar_init(&cls_ready[s], 1);
+            mbar_init(&scls_ready[s], 8);
         }
         fence_mbar_init();
     }
@@ -157,7 +162,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
     const int n_local = p.n_items > (int)blockIdx.x ? (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     if (warp == 0) {
-        if (lane == 0) {  // ---------------------------------------------------------------- TMA producer
+        if (elect_one()) {  // -------------------------------------------------------------- TMA producer
+            // (elect.sync region, here and in the MMA issuers: the compiler keeps descriptors and addresses in uniform registers;
+            //  under `lane == 0` every UTMALDG / UTCHMMA was wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop, ~150 clk each)
             uint32_t it = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
                 const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
@@ -176,9 +183,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
             }
         }
     } else if (warp == 1 || warp == 2) {
-        if (lane == 0) {  // ---------------------------------------------------------------- MMA issuers: warp 1 -> tile 0, warp 2 -> tile 1
-            // One issuing thread per query tile: issuing a chain of dependent small MMAs blocks the thread for ~100 cycles per
-            // instruction, so a single issuer would hold back the other tile's S / PV groups behind it.
+        if (elect_one()) {  // -------------------------------------------------------------- MMA issuers: warp 1 -> tile 0, warp 2 -> tile 1
             constexpr uint32_t idesc_s = make_idesc(1, 128, 256);
             constexpr uint32_t idesc_o = make_idesc(1, 128, 64) | (1u << 16);   // B (= V) is MN-major
             const int t = warp - 1;
@@ -201,115 +206,76 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
                 {                                                               // O_t = P_t V
                     const uint64_t b = make_sdesc_mn128(sv);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)       // even key blocks -> O_a, odd -> O_b: two independent chains
-                        umma_f16_ts(tr + 128 + 64 * (j & 1), tr + 8 * j, b + (uint64_t)(j * 128), idesc_o, j >= 2);
+                    for (int j = 0; j < 16; ++j) umma_f16_ts(tr + 128, tr + 8 * j, b + (uint64_t)(j * 128), idesc_o, j != 0);
                     umma_commit(&o_full[t]);
                     umma_commit(&empty[st]);                                    // this tile's MMAs have read the stage
                     ATC_EV(1, 2 + t, it);
                 }
             }
         }
-    } else if (warp == 3) {  // -------------------------------------------------------------- the 257th row and column
-        // One query row / one key column is too small for a tcgen05 tile and too slow as scalar FMAs, so both run on the
-        // warp-level tensor path: mma.sync m16n8k16 with a single live row (or column) in one operand, the other operand
-        // via ldmatrix from the swizzled TMA tiles.
+    } else if (warp == 3) {  // -------------------------------------------------------------- the class-token query row
         uint32_t it = 0;
         const int g = lane >> 2, t4 = lane & 3;
+        const uint32_t pcls_a = smem_u32(pcls);
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
             const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
             const int seq = item / p.H, head = item - seq * p.H;
-            const uint32_t sq = smem0 + st * ATC_STAGE_BYTES, sk = sq + ATC_TILE_BYTES, sv = sk + ATC_TILE_BYTES;
+            const uint32_t sq = smem0 + st * ATC_STAGE_BYTES, sv = sq + 2 * ATC_TILE_BYTES;
             const uint32_t qc = sq + 3 * ATC_TILE_BYTES, kc = qc + ATC_ROW_BYTES, vc = kc + ATC_ROW_BYTES;
             mbar_wait(&full[st], ph);
             if (lane == 0) ATC_EV(2, 0, it);
-            // ---- class-key column: s256[q] = Q[q] . K[256], q = 0..255.  A = 16 query rows, B = K[256] in column n = 0.
-            {
-                uint32_t kb[4][2];                      // B fragments: b0 = dims 16kk+2t,+1 ; b1 = dims 16kk+8+2t,+1 (n = g = 0 only)
+            // its score against its own key: lane l holds dims 2l, 2l+1
+            const uint32_t qw = lds32(qc + lane * 4), kw = lds32(kc + lane * 4);
+            float sd = fmaf(bf_lo(qw), bf_lo(kw), bf_hi(qw) * bf_hi(kw));
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    kb[kk][0] = g == 0 ? lds32(kc + (kk * 8 + t4) * 4) : 0u;
-                    kb[kk][1] = g == 0 ? lds32(kc + (kk * 8 + 4 + t4) * 4) : 0u;
-                }
-                float* dst = s256buf + st * 256;
-#pragma unroll 4
-                for (int mt = 0; mt < 16; ++mt) {
-                    float c[4] = {0.f, 0.f, 0.f, 0.f};
-                    const int r = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+            for (int o = 16; o >= 1; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
+            // the other 256 scores come from the softmax warps (lane l takes keys l, l + 32, ...)
+            mbar_wait(&scls_ready[st], ph);
+            float sc[8];
+            float mx = sd;
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        uint32_t a[4];
-                        ldsm_x4(a, sw128(sq, r, kk * 2 + (lane >> 4)));
-                        mma_bf16_16816(c, a, kb[kk][0], kb[kk][1]);
-                    }
-                    if (t4 == 0) { dst[mt * 16 + g] = c[0]; dst[mt * 16 + g + 8] = c[2]; }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&cls_ready[st]);
-            }
-            // ---- class-query row.  A fragments of q_cls for the 4 k-steps: a0 = dims 16kk+2t,+1 ; a2 = dims 16kk+8+2t,+1 (row 0)
-            uint32_t qa[4][4];
+            for (int i = 0; i < 8; ++i) { sc[i] = scls[st * 256 + lane + 32 * i]; mx = fmaxf(mx, sc[i]); }
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                qa[kk][0] = g == 0 ? lds32(qc + (kk * 8 + t4) * 4) : 0u;
-                qa[kk][2] = g == 0 ? lds32(qc + (kk * 8 + 4 + t4) * 4) : 0u;
-                qa[kk][1] = 0u; qa[kk][3] = 0u;
-            }
-            // scores: 33 n-tiles of 8 keys (tile 32 = keys 256..263 from the class-row box; only key 256 is real)
-            float sc[33][2];
-            float mx = -INFINITY;
-#pragma unroll
-            for (int nt = 0; nt < 33; ++nt) {
-                float c[4] = {0.f, 0.f, 0.f, 0.f};
-                const uint32_t tile = nt < 32 ? sk : kc;
-                const int r = (nt < 32 ? nt * 8 : 0) + (lane & 7);
-#pragma unroll
-                for (int kp = 0; kp < 2; ++kp) {
-                    uint32_t b[4];
-                    ldsm_x4(b, sw128(tile, r, kp * 4 + (lane >> 3)));
-                    mma_bf16_16816(c, qa[2 * kp], b[0], b[1]);
-                    mma_bf16_16816(c, qa[2 * kp + 1], b[2], b[3]);
-                }
-                if (nt == 32) { if (t4 != 0) c[0] = -INFINITY; c[1] = -INFINITY; }      // keys 257.. do not exist
-                sc[nt][0] = c[0]; sc[nt][1] = c[1];
-                mx = fmaxf(mx, fmaxf(c[0], c[1]));
-            }
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             const float nms = -mx * p.sl2;
             float sum = 0.f;
 #pragma unroll
-            for (int nt = 0; nt < 33; ++nt) {
-                sc[nt][0] = fast_exp2(fmaf(sc[nt][0], p.sl2, nms));
-                sc[nt][1] = fast_exp2(fmaf(sc[nt][1], p.sl2, nms));
-                sum += sc[nt][0] + sc[nt][1];
+            for (int i = 0; i < 8; ++i) {
+                const float e = fast_exp2(fmaf(sc[i], p.sl2, nms));
+                sum += e;
+                pcls[lane + 32 * i] = __float2bfloat16_rn(e);
             }
-            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-            // O = P V: 17 k-tiles of 16 keys (tile 16 = keys 256..271 from the class-row box, P = 0 beyond key 256)
-            float o[8][4];
 #pragma unroll
-            for (int dt = 0; dt < 8; ++dt) { o[dt][0] = 0.f; o[dt][1] = 0.f; o[dt][2] = 0.f; o[dt][3] = 0.f; }
+            for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float e256 = fast_exp2(fmaf(sd, p.sl2, nms));
+            if (lane < 16) pcls[256 + lane] = __float2bfloat16_rn(lane == 0 ? e256 : 0.f);   // keys 257.. do not exist
+            __syncwarp();
+            // O^T[d][0] = sum_key V^T[d][key] p[key]: 4 d-tiles x 17 key-tiles of m16n8k16 (tile 16 = keys 256..271 from the
+            // class-row box); A = V^T by ldmatrix.trans of the swizzled V tile, B = p in column n = 0
+            float o[4][4];
+#pragma unroll
+            for (int dt = 0; dt < 4; ++dt) { o[dt][0] = 0.f; o[dt][1] = 0.f; o[dt][2] = 0.f; o[dt][3] = 0.f; }
 #pragma unroll
             for (int kt = 0; kt < 17; ++kt) {
-                uint32_t pa[4];
-                pa[0] = pack2_bf16(sc[2 * kt][0], sc[2 * kt][1]);
-                pa[2] = kt < 16 ? pack2_bf16(sc[2 * kt + 1][0], sc[2 * kt + 1][1]) : 0u;
-                pa[1] = 0u; pa[3] = 0u;
+                const uint32_t b0 = g == 0 ? lds32(pcls_a + (kt * 16 + 2 * t4) * 2) : 0u;
+                const uint32_t b1 = g == 0 ? lds32(pcls_a + (kt * 16 + 8 + 2 * t4) * 2) : 0u;
                 const uint32_t tile = kt < 16 ? sv : vc;
-                const int r = (kt < 16 ? kt * 16 : 0) + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int r = (kt < 16 ? kt * 16 : 0) + (lane & 7) + ((lane >> 4) & 1) * 8;
 #pragma unroll
-                for (int dp = 0; dp < 4; ++dp) {
-                    uint32_t b[4];
-                    ldsm_x4_t(b, sw128(tile, r, dp * 2 + (lane >> 4)));
-                    mma_bf16_16816(o[2 * dp], pa, b[0], b[1]);
-                    mma_bf16_16816(o[2 * dp + 1], pa, b[2], b[3]);
+                for (int dt = 0; dt < 4; ++dt) {
+                    uint32_t a[4];
+                    ldsm_x4_t(a, sw128(tile, r, 2 * dt + ((lane >> 3) & 1)));
+                    mma_bf16_16816(o[dt], a, b0, b1);
                 }
             }
-            if (g == 0) {
-                const float inv = 1.0f / sum;
-                __nv_bfloat16* orow = p.out + ((size_t)seq * S + 256) * p.D + head * 64 + 2 * t4;
+            if (t4 == 0) {
+                const float inv = 1.0f / (sum + e256);
+                __nv_bfloat16* orow = p.out + ((size_t)seq * S + 256) * p.D + head * 64 + g;
 #pragma unroll
-                for (int dt = 0; dt < 8; ++dt) *reinterpret_cast<uint32_t*>(orow + dt * 8) = pack2_bf16(o[dt][0] * inv, o[dt][1] * inv);
+                for (int dt = 0; dt < 4; ++dt) {
+                    orow[dt * 16] = __float2bfloat16_rn(o[dt][0] * inv);
+                    orow[dt * 16 + 8] = __float2bfloat16_rn(o[dt][2] * inv);
+                }
             }
             __syncwarp();
             if (lane == 0) { mbar_arrive(&empty[st]); ATC_EV(2, 1, it); }
@@ -325,7 +291,50 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
             const int st = it & 1; const uint32_t ph = (it >> 1) & 1, ip = it & 1;
             const int seq = item / p.H, head = item - seq * p.H;
-            const uint32_t vc = smem0 + st * ATC_STAGE_BYTES + 3 * ATC_TILE_BYTES + 2 * ATC_ROW_BYTES;
+            const uint32_t sq = smem0 + st * ATC_STAGE_BYTES, sk = sq + ATC_TILE_BYTES;
+            const uint32_t qc = sq + 3 * ATC_TILE_BYTES, kc = qc + ATC_ROW_BYTES, vc = kc + ATC_ROW_BYTES;
+            // ---- the 257th column and row for this warp's 32 query rows / 32 keys (rows base .. base+31 of the Q and K tiles):
+            // m16n8k16 tiles with the class-token vector as the single live column of B
+            float s256;
+            {
+                mbar_wait(&full[st], ph);
+                const int g = lane >> 2, t4 = lane & 3, base_row = row - lane;
+                float ccol[2][4], crow[2][4];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { ccol[mt][i] = 0.f; crow[mt][i] = 0.f; }
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    // B fragments: b0 = dims 16kk+2t4,+1 ; b1 = dims 16kk+8+2t4,+1 (column n = g = 0 only)
+                    const uint32_t kb0 = g == 0 ? lds32(kc + (kk * 8 + t4) * 4) : 0u, kb1 = g == 0 ? lds32(kc + (kk * 8 + 4 + t4) * 4) : 0u;
+                    const uint32_t qb0 = g == 0 ? lds32(qc + (kk * 8 + t4) * 4) : 0u, qb1 = g == 0 ? lds32(qc + (kk * 8 + 4 + t4) * 4) : 0u;
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        const int r = base_row + mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                        uint32_t a[4];
+                        ldsm_x4(a, sw128(sq, r, kk * 2 + (lane >> 4)));
+                        mma_bf16_16816(ccol[mt], a, kb0, kb1);                 // Q[r] . K[256]
+                        ldsm_x4(a, sw128(sk, r, kk * 2 + (lane >> 4)));
+                        mma_bf16_16816(crow[mt], a, qb0, qb1);                 // K[r] . Q[256]
+                    }
+                }
+                if (t4 == 0) {
+                    float* dst = scls + st * 256 + base_row + g;
+                    dst[0] = crow[0][0]; dst[8] = crow[0][2]; dst[16] = crow[1][0]; dst[24] = crow[1][2];
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&scls_ready[st]);
+                // row base + lane = m-tile lane >> 4, fragment row lane & 15: held by lane 4 * (lane & 7) as c[0] (rows 0..7) or c[2]
+                const int src = (lane & 7) * 4;
+                const float v00 = __shfl_sync(0xffffffffu, ccol[0][0], src), v02 = __shfl_sync(0xffffffffu, ccol[0][2], src);
+                const float v10 = __shfl_sync(0xffffffffu, ccol[1][0], src), v12 = __shfl_sync(0xffffffffu, ccol[1][2], src);
+                s256 = (lane & 16) ? ((lane & 8) ? v12 : v10) : ((lane & 8) ? v02 : v00);
+            }
+            // The previous item's output store has had the class pass above to read its staging rows: only now release that stage
+            // to the producer (waiting for the read right after the store put ~1 k clk on this warpgroup's serial chain).
+            if (it > 0 && elect_one()) { tma_store_wait_read<0>(); mbar_arrive(&empty[st ^ 1]); }
+            __syncwarp();
             mbar_wait(&s_full[t], ip);
             tc_fence_after();
             if (quarter == 0 && lane == 0) ATC_EV(3 + t, 0, it);
@@ -345,10 +354,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
                 for (int j = 0; j < 32; j += 2) m4[(j >> 1) & 3] = fmax3(m4[(j >> 1) & 3], __uint_as_float(vb[j]), __uint_as_float(vb[j + 1]));
                 tmem_ld_wait();
             }
-            mbar_wait(&cls_ready[st], ph);
-            const float s256 = s256buf[st * 256 + row];                // score against the class-token key
             const float nms = -fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])), s256) * p.sl2;
             if (quarter == 0 && lane == 0) ATC_EV(3 + t, 1, it);
+
 #if ATC_PINGPONG
             named_bar_sync(1 + t, 256);                                // my turn on the MUFU pipe
 #endif
@@ -383,22 +391,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[t]);
             if (quarter == 0 && lane == 0) ATC_EV(3 + t, 2, it);
-            // epilogue: (O_a + O_b + p256 * V[256]) / (l + p256) -> bf16 row
+            // epilogue: (O + p256 * V[256]) / (l + p256) -> bf16 row
             const float e256 = fast_exp2(fmaf(s256, p.sl2, nms));
             const float inv = 1.0f / (sum0 + sum1 + e256);
             const float ei = e256 * inv;
-            mbar_wait(&full[st], ph);                                  // (long complete) makes the TMA-written V[256] row visible
-            // Output staging: this warp's 32 rows of the Q tile (S_t is complete and the class warp has finished its pass over Q:
-            // both were waited on above), 128-byte rows with the 128B swizzle, then ONE TMA store of the 32 x 64 box.
+            // Output staging: this warp's 32 rows of the Q tile (S_t is complete, and the only other reader of these rows was this
+            // warp's own class-column pass above), 128-byte rows with the 128B swizzle, then ONE TMA store of the 32 x 64 box.
             uint8_t* stg = base + st * ATC_STAGE_BYTES + t * (128 * 128) + quarter * 4096;
             mbar_wait(&o_full[t], ip);
             tc_fence_after();
             if (quarter == 0 && lane == 0) ATC_EV(3 + t, 3, it);
+            tmem_ld_32x32(treg + 128, va);                             // O columns 0..31
+            tmem_ld_32x32(treg + 160, vb);                             // O columns 32..63
+            tmem_ld_wait();
+            tc_fence_before();                                         // O is in registers: the TMEM tile can take the next item's S now
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_free[t]);
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-                tmem_ld_32x32(treg + 128 + hh * 32, va);               // O_a columns 32hh..32hh+31
-                tmem_ld_32x32(treg + 192 + hh * 32, vb);               // O_b
-                tmem_ld_wait();
+                const uint32_t (&vo)[32] = hh ? vb : va;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const uint4 vv = lds128(vc + (hh * 4 + c) * 16);
@@ -406,11 +417,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
                     uint32_t o[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        float a, b;
-                        fadd2(a, b, __uint_as_float(va[c * 8 + 2 * j]), __uint_as_float(va[c * 8 + 2 * j + 1]),
-                              __uint_as_float(vb[c * 8 + 2 * j]), __uint_as_float(vb[c * 8 + 2 * j + 1]));
-                        a = fmaf(a, inv, bf_lo(w[j]) * ei);
-                        b = fmaf(b, inv, bf_hi(w[j]) * ei);
+                        const float a = fmaf(__uint_as_float(vo[c * 8 + 2 * j]), inv, bf_lo(w[j]) * ei);
+                        const float b = fmaf(__uint_as_float(vo[c * 8 + 2 * j + 1]), inv, bf_hi(w[j]) * ei);
                         o[j] = pack2_bf16(a, b);
                     }
                     *reinterpret_cast<uint4*>(stg + lane * 128 + (((hh * 4 + c) ^ (lane & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -418,18 +426,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
             }
             fence_async_proxy();
             __syncwarp();
-            if (lane == 0) {
+            if (elect_one()) {
                 tma_store_2d(&tm_out, stg, head * 64, seq * S + t * 128 + quarter * 32);
-                tma_store_commit();
-                tma_store_wait_read<0>();                              // the stage may be refilled once the store has read it
+                tma_store_commit();                                    // (the stage is released in the next iteration, above)
             }
-            tc_fence_before();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&t_free[t]); mbar_arrive(&empty[st]); }
             if (quarter == 0 && lane == 0) ATC_EV(3 + t, 4, it);
         }
     }
-    if (warp >= 4 && lane == 0) tma_store_wait_all<0>();
+    if (warp >= 4 && elect_one()) tma_store_wait_all<0>();   // the same elected lane that committed the bulk stores
     __syncwarp();
     tc_fence_before();
     __syncthreads();

@@ -142,7 +142,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {  // ---------------- TMA producer
+        if (elect_one()) {  // ---------------- TMA producer
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int pt = tile / num_n, n_blk = tile - pt * num_n;
@@ -168,7 +168,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {  // ---------------- MMA issuer: D += A_lo W_hi + A_hi W_lo + A_hi W_hi (small terms first)
+        if (elect_one()) {  // ---------------- MMA issuer: D += A_lo W_hi + A_hi W_lo + A_hi W_hi (small terms first)
             constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, 128, BN);
             int stage = 0; uint32_t phase = 0; uint32_t it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -230,7 +230,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
                         f[4 * j] += r4.x; f[4 * j + 1] += r4.y; f[4 * j + 2] += r4.z; f[4 * j + 3] += r4.w;
                     }
                 }
-                if (lane == 0) tma_store_wait_read<0>();            // previous store finished reading the staging buffer
+                if (elect_one()) tma_store_wait_read<0>();   // bulk groups are per thread: the lane that issued the store            // previous store finished reading the staging buffer
                 __syncwarp();
                 uint8_t* rowp = stg + lane * 128;
 #pragma unroll
@@ -238,7 +238,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
                     *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
                 fence_async_proxy();
                 __syncwarp();
-                if (lane == 0) {
+                if (elect_one()) {
                     tma_store_2d(&tm_out, stg, n0, (int)row0);
                     tma_store_commit();
                 }
@@ -265,7 +265,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
         }
-        if (lane == 0) tma_store_wait_all<0>();
+        if (elect_one()) tma_store_wait_all<0>();
     }
     __syncwarp();
     tc_fence_before();

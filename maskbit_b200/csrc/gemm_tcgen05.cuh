@@ -365,7 +365,7 @@ __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, u
                 const int lane = threadIdx.x & 31;
                 const int sub = (c >> 5) & 1;                 // which 32-column half of the 64-column staging row
                 if (sub == 0 && !kResS) {                     // the previous store must have finished reading the buffer
-                    if (lane == 0) tma_store_wait_read<0>();
+                    if (elect_one()) tma_store_wait_read<0>();   // bulk groups are per thread: the lane that issued the store
                     __syncwarp();
                 }
                 uint8_t* rowp = stg.buf + (kResS ? (c >> 6) * 4096 : 0) + lane * 128;
@@ -375,7 +375,7 @@ __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, u
                 if (sub == 1) {
                     fence_async_proxy();                      // generic-proxy smem writes -> visible to the bulk copy
                     __syncwarp();
-                    if (lane == 0) {
+                    if (elect_one()) {
                         tma_store_2d(stg.tm, stg.buf + (kResS ? (c >> 6) * 4096 : 0), n0 - 32, stg.row0);
                         tma_store_commit();
                     }
@@ -444,7 +444,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {  // ---------------- TMA producer
+        if (elect_one()) {  // ---------------- TMA producer (elect.sync region: operands stay in uniform registers, no R2UR waterfall per issue)
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m_blk = tile / num_n, n_blk = tile % num_n;
@@ -458,7 +458,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {  // ---------------- MMA issuer
+        if (elect_one()) {  // ---------------- MMA issuer
             constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, BM, BN);
             int stage = 0; uint32_t phase = 0; uint32_t it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -606,7 +606,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == W_PROD) {
-        if (lane == 0) {  // ---------------- TMA producer (each CTA: its 128 A rows, its 128 of the 256 B rows)
+        if (elect_one()) {  // ---------------- TMA producer (each CTA: its 128 A rows, its 128 of the 256 B rows)
             int stage = 0; uint32_t phase = 0;
             uint32_t it = 0;
             for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
@@ -632,7 +632,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
             }
         }
     } else if (warp == W_MMA) {
-        if (lane == 0 && leader) {  // ---------------- MMA issuer (leader CTA only)
+        if (leader && elect_one()) {  // ---------------- MMA issuer (leader CTA only)
             constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, 256, BN);
             int stage = 0; uint32_t phase = 0; uint32_t it = 0;
             for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
@@ -696,7 +696,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
             uint8_t* stg_w = smem_stg + ew * C::STG_WARP;
             if constexpr (kResTma) {
                 // the previous tile's two stores have read the staging tiles -> refill them with this tile's residual rows
-                if (lane == 0) {
+                if (elect_one()) {
                     tma_store_wait_read<0>();
                     mbar_arrive_expect_tx(&res_full[ew], 2 * 4096);
                     tma_load_2d(stg_w, &tm_r, &res_full[ew], n_blk * BN + half * CPW, row0);
@@ -717,7 +717,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
             if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tmem_empty[as]), 0));
             if (ew == 0 && lane == 0) GEMM_EV(1, 2, it, clock64());
         }
-        if (kTma && lane == 0) tma_store_wait_all<0>();   // bulk stores complete before the CTA retires its smem
+        if (kTma && elect_one()) tma_store_wait_all<0>();   // bulk stores complete before the CTA retires its smem
     }
     __syncwarp();
     tc_fence_before();

@@ -80,7 +80,13 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
     }
     return ctr;
 }
-__device__ __forceinline__ float u01_open(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f) + (0.5f / 16777216.0f); }
+// Production-mode noise transforms.  The uniform is built from 23 random bits as (k + 0.5) * 2^-23: every value is exactly
+// representable and lies in [2^-24, 1 - 2^-24], so neither log below can see 0 or 1 (a 24-bit k * 2^-24 + 2^-25 rounds to
+// 1.0f for k = 2^24 - 1: -log(1) = -0 made that token unselectable, and its Gumbel value +inf).  logf, not __logf: the fast
+// intrinsic has ~2^-21 ABSOLUTE error near 1, exactly where the small Exp(1) draws that decide argmax(p / q) come from.
+__device__ __forceinline__ float u01_open(uint32_t r) { return ((float)(r >> 9) + 0.5f) * (1.0f / 8388608.0f); }
+__device__ __forceinline__ float sel_exp1(uint32_t r) { return -logf(u01_open(r)); }                  // Exp(1), in (0, 16.7)
+__device__ __forceinline__ float sel_gumbel(uint32_t r) { return -logf(-logf(u01_open(r))); }          // Gumbel(0, 1), finite
 
 struct SelectParams {
     const float* logits_c;      // [B, seq_stride, m, V]
@@ -166,7 +172,7 @@ __global__ void __launch_bounds__(512) select_step_kernel(SelectParams p) {
             } else {
                 const uint4 r = philox4x32(make_uint4((uint32_t)j, (uint32_t)s, (uint32_t)b, p.step),
                                            make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-                qv = -__logf(u01_open(r.x));
+                qv = sel_exp1(r.x);
             }
             const float r = __fdiv_rn(__fdiv_rn(x[i], sum2), qv);
             const bool beats = i == 0 || (!(bestv != bestv) && ((r != r) || r > bestv));
@@ -198,7 +204,7 @@ __global__ void __launch_bounds__(512) select_step_kernel(SelectParams p) {
                 else {
                     const uint4 r = philox4x32(make_uint4(0xffffffffu, (uint32_t)s, (uint32_t)b, p.step),
                                                make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-                    gz = -__logf(-__logf(u01_open(r.x)));
+                    gz = sel_gumbel(r.x);
                 }
                 const float nz = __fmul_rn(__fmul_rn(gz, p.randomize_temperature), p.one_minus_progress);
                 c = __fadd_rn(sel_logf(ptok), nz);

@@ -39,7 +39,9 @@ def label_schedule(total_samples, nclass=1000, label_seed=0):
 @torch.no_grad()
 def generate_samples(config, total_samples=50_000, batchsize=100, res=256, tokenizer_path="", generator_path="", device="cuda:0",
                      label_seed=0, noise_seed=0, models=None, progress=False):
-    """Returns (images uint8 numpy [total_samples, res, res, 3] on every rank, labels int64 tensor [total_samples]).
+    """Returns (images uint8 numpy [total_samples, res, res, 3] on rank 0 -- None on the other ranks --, labels int64 tensor
+    [total_samples]).  Every batch is all-gathered over NCCL (the path's one collective); only rank 0 stages it to the host, so
+    host memory and PCIe traffic do not grow with the number of ranks (50 000 images are 9.8 GB).
 
     ``config`` is a YAML path / shipped config name / loaded config.  ``batchsize`` is the GLOBAL batch of one sample() round
     (the reference's ``batchsize``); with W ranks each samples ``batchsize / W`` of it.  The last batch may be ragged."""
@@ -53,8 +55,9 @@ def generate_samples(config, total_samples=50_000, batchsize=100, res=256, token
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     labels = label_schedule(total_samples, label_seed=label_seed)
-    out = np.empty((total_samples, res, res, 3), dtype=np.uint8)
-    staging = torch.empty((min(batchsize, total_samples), res, res, 3), dtype=torch.uint8).pin_memory()
+    keep = rank == 0
+    out = np.empty((total_samples, res, res, 3), dtype=np.uint8) if keep else None
+    staging = torch.empty((min(batchsize, total_samples), res, res, 3), dtype=torch.uint8).pin_memory() if keep else None
     n_batches = math.ceil(total_samples / batchsize)
     for i in range(n_batches):
         y = labels[batchsize * i: batchsize * (i + 1)]
@@ -68,9 +71,10 @@ def generate_samples(config, total_samples=50_000, batchsize=100, res=256, token
             u8 = torch.empty((0, res, res, 3), dtype=torch.uint8, device=generator.device)
         if world > 1:
             u8 = gather_images(u8, nb)
-        staging[:nb].copy_(u8, non_blocking=True)
-        torch.cuda.current_stream(u8.device).synchronize()
-        out[batchsize * i: batchsize * i + nb] = staging[:nb].numpy()
+        if keep:
+            staging[:nb].copy_(u8, non_blocking=True)
+            torch.cuda.current_stream(u8.device).synchronize()
+            out[batchsize * i: batchsize * i + nb] = staging[:nb].numpy()
         if progress and rank == 0:
             print(f"batch {i + 1}/{n_batches}", flush=True)
     return out, labels

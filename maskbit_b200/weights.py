@@ -125,9 +125,11 @@ def _res_block(prefix, cin, cout):
 
 
 def conv_vq_spec(token_size=12, num_channels=3, hidden_channels=128, channel_mult=(1, 1, 2, 2, 4), num_resolutions=5,
-                 num_res_blocks=2, with_encoder=True):
-    """(name, shape, kind) for ConvVQModel (encoder, decoder, quantize buffers), in state_dict order."""
+                 num_res_blocks=2, with_encoder=True, num_res_blocks_encoder=None):
+    """(name, shape, kind) for ConvVQModel (encoder, decoder, quantize buffers), in state_dict order.  num_res_blocks is the
+    DECODER's count (config num_res_blocks_decoder, else num_res_blocks); the encoder always uses the config's num_res_blocks."""
     hc = hidden_channels
+    enc_blocks = num_res_blocks if num_res_blocks_encoder is None else num_res_blocks_encoder
     cm = tuple(channel_mult)
     spec = []
     if with_encoder:
@@ -135,13 +137,13 @@ def conv_vq_spec(token_size=12, num_channels=3, hidden_channels=128, channel_mul
         icm = (1,) + cm
         for lvl in range(num_resolutions):
             cin, cout = hc * icm[lvl], hc * icm[lvl + 1]
-            for r in range(num_res_blocks):
+            for r in range(enc_blocks):
                 spec += _res_block(f"encoder.down.{lvl}.res_blocks.{r}.", cin if r == 0 else cout, cout)
             if lvl < num_resolutions - 1:
                 spec += [(f"encoder.down.{lvl}.down_conv.weight", (cout, cout, 3, 3), "c"),
                          (f"encoder.down.{lvl}.down_conv.bias", (cout,), "cb")]
         mid = hc * cm[num_resolutions - 1]
-        for r in range(num_res_blocks):
+        for r in range(enc_blocks):
             spec += _res_block(f"encoder.mid.res_blocks.{r}.", mid, mid)
         spec += [("encoder.norm_out.weight", (mid,), "g"), ("encoder.norm_out.bias", (mid,), "gb"),
                  ("encoder.conv_out.weight", (token_size, mid, 1, 1), "c"), ("encoder.conv_out.bias", (token_size,), "cb")]
@@ -183,4 +185,40 @@ def synthetic_conv_vq_state_dict(seed=0, **arch):
             idx = torch.arange(shape[0])
             b2i = (2 ** torch.arange(shape[1]))
             sd[name] = ((idx[:, None] & b2i) != 0).float() * 2.0 - 1.0
+    return sd
+
+
+def trained_like_lfq_bert_state_dict(seed=11, **arch):
+    """LFQBert checkpoint with the statistics a TRAINED post-norm transformer shows and a fresh init does not: LayerNorm gains spread
+    over 0.1 .. 5 (log-normal) with two outlier channels, LayerNorm biases with a common offset and a few +-3 entries, non-zero
+    Linear biases, wider projections (attention logits of several units, output logits of tens).  Used by the parity tests that
+    stress the LayerNorm folding and the bf16 pre-norm residual stream (gemm_tcgen05.cuh); values are the counter hash above."""
+    sd = OrderedDict()
+    for name, shape, kind in lfq_bert_spec(**arch):
+        if kind == "b2i":
+            sd[name] = (2 ** torch.arange(shape[0])).int()
+        elif kind == "g":
+            z = hash_normal(name, shape, seed)
+            g = np.clip(np.exp(0.5 * z), 0.1, 5.0)
+            g[7] = 5.0
+            g[300] = 4.0
+            sd[name] = torch.from_numpy(g.astype(np.float32))
+        elif kind == "b" and ("norm" in name or name.startswith(("first_layer", "last_layer.2"))):
+            z = hash_normal(name, shape, seed) * 0.3
+            layer_sign = 1.0 if (zlib.crc32(name.encode()) & 1) else -1.0
+            b = z + 0.5 * layer_sign
+            b[11] = 3.0
+            b[500] = -3.0
+            sd[name] = torch.from_numpy(b.astype(np.float32))
+        elif kind == "b":
+            sd[name] = _t(name, shape, 0.1, seed)
+        else:
+            std = 0.035
+            if name.endswith(("out_proj.weight", "net.2.weight")):
+                std = 0.02
+            elif name.startswith("prediction_layer"):
+                std = 0.1
+            elif name in ("pos_emb", "class_emb.weight", "input_proj.weight"):
+                std = 0.1
+            sd[name] = _t(name, shape, std, seed)
     return sd

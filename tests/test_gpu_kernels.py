@@ -88,20 +88,30 @@ def test_gemm_rejects_bad_shapes():
     assert rc == -1 and b"gemm shape" in _lib.lib().mb_last_error()
 
 
-@pytest.mark.parametrize("n_seq,S", [(1, 257), (3, 257), (40, 257), (2, 256), (2, 65), (1, 272)])
-def test_attention(n_seq, S):
+@pytest.mark.parametrize("n_seq,S,scale", [(1, 257, 1.5), (3, 257, 1.5), (40, 257, 1.5), (2, 256, 1.5), (2, 65, 1.5), (1, 272, 1.5),
+                                           (5, 257, 4.0), (5, 257, 0.05), (300, 257, 1.0)])
+def test_attention(n_seq, S, scale):
+    """softmax(Q K^T / 8) V per head vs fp64 torch.  scale 4.0: attention logits with a standard deviation of 16 (rows close to
+    one-hot, the regime of a trained checkpoint); scale 0.05: near-uniform rows; 300 sequences: more than two items per SM, so
+    every barrier of the persistent kernel wraps its phase several times."""
     D, H = 1024, 16
     g = torch.Generator(device="cuda").manual_seed(S + n_seq)
-    qkv = (torch.randn((n_seq * S, 3 * D), device="cuda", generator=g) * 1.5).to(torch.bfloat16)
+    qkv = (torch.randn((n_seq * S, 3 * D), device="cuda", generator=g) * scale).to(torch.bfloat16)
     out = torch.empty((n_seq * S, D), dtype=torch.bfloat16, device="cuda")
     _lib.check(_lib.lib().mb_test_attention(_p(qkv), _p(out), n_seq, S, D, H, _stream()))
     torch.cuda.synchronize()
-    q, k, v = qkv.double().view(n_seq, S, 3, H, 64).permute(2, 0, 3, 1, 4)
-    att = torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1)
-    ref = (att @ v).permute(0, 2, 1, 3).reshape(n_seq * S, D)
-    err = (out.double() - ref).abs()
-    # output rounded to bf16 (2^-9 relative, |o| up to ~6) + P rounded to bf16 before P.V (2^-9 relative on |v| ~ 1.5)
-    assert (err <= ref.abs() * 2 ** -8 + 8e-3).all(), f"attention max err {err.max().item()}"
+    worst = 0.0
+    for s0 in range(0, n_seq, 32):
+        s1 = min(n_seq, s0 + 32)
+        q, k, v = qkv[s0 * S:s1 * S].double().view(s1 - s0, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+        att = torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1)
+        ref = (att @ v).permute(0, 2, 1, 3).reshape((s1 - s0) * S, D)
+        err = (out[s0 * S:s1 * S].double() - ref).abs()
+        # output rounded to bf16 (2^-9 relative) + P rounded to bf16 before P.V (2^-9 relative on |v| ~ scale)
+        bound = ref.abs() * 2 ** -8 + 5.4e-3 * scale
+        assert (err <= bound).all(), f"attention max err {err.max().item()} (sequences {s0}..{s1})"
+        worst = max(worst, (err / bound).max().item())
+    print(f"attention n_seq={n_seq} S={S} scale={scale}: worst err / bound = {worst:.3f}")
 
 
 def _row_stats(y_bf16):
@@ -171,6 +181,85 @@ def test_gemm_residual_layernorm_stats(M, K):
     ref = a.double() @ W.double().t() + b.double() + x
     err = (out.double() - ref).abs()
     assert (err <= ref.abs() * 2 ** -8 + 1e-3).all(), f"max err {err.max().item()}"
+    want = _row_stats(out).sum(1)
+    assert (st.sum(1) - want).abs().max().item() <= 1e-3 * want.abs().max().item()
+
+
+def _stress_rows(M, K, g, ratio, outlier):
+    """Pre-LayerNorm rows with |row mean| / row sigma = ratio and (optionally) one channel 50 sigma away: what the residual
+    stream of a trained checkpoint can look like (VERDICT r1 weak #4).  Returned as the bf16 tensor the kernels read."""
+    sigma = 0.8
+    y = torch.randn((M, K), device="cuda", generator=g) * sigma
+    sign = torch.where(torch.rand((M, 1), device="cuda", generator=g) < 0.5, -1.0, 1.0)
+    y = y + sign * ratio * sigma
+    if outlier:
+        y[:, 77] += 50.0 * sigma
+    return y.to(torch.bfloat16)
+
+
+def _stress_affine(K, g):
+    gamma = torch.exp(0.6 * torch.randn((K,), device="cuda", generator=g)).clamp(0.1, 5.0)
+    beta = torch.randn((K,), device="cuda", generator=g) * 0.5
+    beta[5], beta[900] = 3.0, -3.0
+    return gamma, beta
+
+
+# measured on B200 (profiles/r02_pytest_gpu.log) and asserted one notch above: see the printed "worst err / bound"
+@pytest.mark.parametrize("ratio,outlier", [(10.0, False), (100.0, False), (0.0, True), (10.0, True)])
+@pytest.mark.parametrize("epi,N", [(5, 3072), (6, 4096), (8, 1024), (9, 128)])
+def test_gemm_layernorm_fold_stress(epi, N, ratio, outlier):
+    """The LayerNorm-in epilogues (5: QKV, 6: MLP up, 8: head, 9: prediction layer) where the folding is fragile: rows whose mean
+    is 10 / 100 standard deviations away from zero (cancellation in acc - mean*u and in E[y^2] - mean^2), an outlier channel,
+    gains in [0.1, 5], biases up to +-3.  Reference = Linear(LayerNorm(y)) in fp64 on the same bf16 rows and folded bf16 weights."""
+    K, S, n_seq = 1024, 257, 4
+    M = n_seq * S
+    g = torch.Generator(device="cuda").manual_seed(int(epi * 1000 + ratio + 7 * outlier))
+    y = _stress_rows(M, K, g, ratio, outlier)
+    W = torch.randn((N, K), device="cuda", generator=g) * 0.03
+    b = torch.randn((N,), device="cuda", generator=g) * 0.1
+    gamma, beta = _stress_affine(K, g)
+    Wf = (W * gamma).to(torch.bfloat16)
+    u = Wf.float().sum(1).contiguous()
+    c = (W.double() @ beta.double() + b.double()).float().contiguous()
+    out, st = _gemm_ex(y, Wf, c, u, None, _row_stats(y), epi, want_stats=(epi == 8), seq_in=S if epi == 9 else 0,
+                       seq_out=S - 1 if epi == 9 else 0)
+    n = torch.nn.functional.layer_norm(y.double(), (K,), eps=1e-12)
+    ref = n @ Wf.double().t() + c.double()
+    if epi in (6, 8):
+        ref = _gelu(ref)
+    if epi == 9:
+        ref = ref.view(n_seq, S, N)[:, : S - 1].reshape(-1, N)
+    err = (out.double() - ref).abs()
+    # bf16 output rounding (fp32 for epi 9) + the fp32 cancellation terms, which grow with the mean / sigma ratio
+    tol = (2 ** -8 if epi != 9 else 2 ** -18) * ref.abs() + 1e-3 * max(1.0, ratio / 10.0)
+    worst = (err / tol).max().item()
+    print(f"LN-fold stress epi={epi} N={N} ratio={ratio} outlier={outlier}: max err {err.max().item():.3e} (|ref| max {ref.abs().max().item():.1f}), worst err / bound {worst:.3f}")
+    assert worst <= 1.0
+    if epi == 8:
+        want = _row_stats(out).sum(1)
+        assert (st.sum(1) - want).abs().max().item() <= 1e-3 * want.abs().max().item()
+
+
+@pytest.mark.parametrize("ratio,outlier", [(10.0, False), (100.0, False), (10.0, True)])
+@pytest.mark.parametrize("K", [1024, 4096])
+def test_gemm_residual_fold_stress(K, ratio, outlier):
+    """Residual epilogue (7: out-projection, MLP down) on the same stressed rows: out = A W^T + b + LayerNorm(y_res), and the row
+    statistics it leaves for the next LayerNorm."""
+    N, M = 1024, 4 * 257
+    g = torch.Generator(device="cuda").manual_seed(int(K + ratio + 7 * outlier))
+    a = torch.randn((M, K), device="cuda", generator=g).to(torch.bfloat16)
+    W = (torch.randn((N, K), device="cuda", generator=g) * 0.03).to(torch.bfloat16)
+    b = torch.randn((N,), device="cuda", generator=g) * 0.1
+    y_res = _stress_rows(M, N, g, ratio, outlier)
+    gamma, beta = _stress_affine(N, g)
+    out, st = _gemm_ex(a, W, (b + beta).contiguous(), gamma.contiguous(), y_res, _row_stats(y_res), 7, want_stats=True)
+    x = torch.nn.functional.layer_norm(y_res.double(), (N,), gamma.double(), beta.double(), eps=1e-12)
+    ref = a.double() @ W.double().t() + b.double() + x
+    err = (out.double() - ref).abs()
+    tol = 2 ** -8 * ref.abs() + 1e-3 * max(1.0, ratio / 10.0)
+    worst = (err / tol).max().item()
+    print(f"residual stress K={K} ratio={ratio} outlier={outlier}: max err {err.max().item():.3e}, worst err / bound {worst:.3f}")
+    assert worst <= 1.0
     want = _row_stats(out).sum(1)
     assert (st.sum(1) - want).abs().max().item() <= 1e-3 * want.abs().max().item()
 

@@ -21,6 +21,10 @@ from maskbit_b200.masking import step_tables
 from oracle import maskbit_oracle as O
 from oracle import select_oracle as SO
 
+import sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import select_cases as SC  # noqa: E402
+
 pytestmark = pytest.mark.gpu
 
 # bf16 GEMM operands / bf16 residual stream with fp32 accumulation, LayerNorm and softmax, vs the fp32 reference:
@@ -28,6 +32,10 @@ pytestmark = pytest.mark.gpu
 LOGIT_MAX_ABS = 6e-2
 LOGIT_MEAN_ABS = 1e-2
 PIXEL_MAX_ABS = 1e-3   # BASELINE.json north_star: decoded pixels within 1e-3 abs fp32
+STEP0_AGREEMENT_MIN = 0.95        # free-running step 0 vs the reference's tokens (argmax(p/q) flips under bf16 logits)
+TEACHER_FORCED_AGREEMENT_MIN = 0.90
+TRAINED_LIKE_MAX_REL = 2e-2       # trained-like checkpoint: max / mean logit error relative to the logit range
+TRAINED_LIKE_MEAN_REL = 3e-3
 
 
 def _p(t):
@@ -235,6 +243,88 @@ def test_select_random_vs_c_oracle(V, B, guided, temperature):
         assert torch.equal(out.cpu()[keep], tok[keep])
 
 
+@pytest.mark.parametrize("name", list(SC.CASES))
+def test_select_stub_cases_match_reference(name, golden_dir):
+    """The reference's own select code (sampling.py:90-131), run through sample() on a stub generator with seeded logits
+    (tests/select_cases.py, fixture tests/golden/select_stub.npz): 270 k decisions over V = 32 .. 512, guided and unguided,
+    annealed temperature, peaked logits (range of tens: exp underflow, p == 0, log(0) confidences).  mb_select_step reproduces
+    every predicted token, chaining on its own re-masked state.  Mismatch budget: 0."""
+    g = np.load(os.path.join(golden_dir, "select_stub.npz"))
+    case = SC.CASES[name]
+    kw, guided, logits, qs, gs, dg = SC.case_inputs(case)
+    assert dg == str(g[name + "_digest"]), "regenerated inputs differ from the ones the fixture was recorded on"
+    ref = torch.from_numpy(g[name + "_tokens"].astype(np.int64)).cuda()
+    B, steps = case["B"], case["steps"]
+    scale, temp, omp, mask_len = step_tables(steps, 512, softmax_temperature=kw["softmax_temperature"],
+                                             mask_schedule_strategy=kw["mask_schedule_strategy"], guidance_scale=kw["guidance_scale"],
+                                             guidance_annealing=kw["guidance_annealing"], scale_pow=kw["scale_pow"],
+                                             use_sampling_annealing=kw["use_sampling_annealing"])
+    _, _, _, gen = models(case["bits"])
+    masked = torch.full((B, 256, 2), kw["mask_token"], dtype=torch.int64, device="cuda")
+    mismatches = 0
+    for i in range(steps):
+        lc, lu = logits[i]
+        pred, masked = select_step(gen, lc.cuda(), lu.cuda() if guided else None, qs[i].cuda(), gs[i].cuda(), masked, scale=scale[i],
+                                   temperature=temp[i], rt=kw["randomize_temperature"], omp=omp[i], mask_len=mask_len[i], step=i)
+        mismatches += int((pred != ref[i]).sum())
+    print(f"select stub case {name}: V={2 ** (case['bits'] // 2)} decisions={ref.numel()} mismatches vs the reference={mismatches}")
+    assert mismatches == 0
+
+
+@pytest.mark.parametrize("V", [32, 64, 128, 256, 512])
+def test_select_vs_torch_oracle(V):
+    """mb_select_step against the TORCH oracle O.select_step (pinned to the reference, and executing torch's own vectorised
+    exp / log / sort like the reference does) on seeded inputs at every shipped vocabulary -- not against its plain-C twin.
+    Three chained steps from a partially decoded state.  Mismatch budget: 0 (count printed)."""
+    _, kw, _, gen = models(12)
+    B, n, m = 6, 256, 2
+    gcpu = torch.Generator().manual_seed(V * 7 + 1)
+    tok = torch.randint(0, V, (B, n, m), generator=gcpu)
+    for b in range(B):
+        tok[b].view(-1)[torch.randperm(n * m, generator=gcpu)[:400]] = V
+    masked_t, masked_d = tok.clone(), tok.cuda()
+    total = mism = 0
+    for i, (mask_len, omp, scale, temperature) in enumerate([(333.0, 0.7, 1.9, 1.0), (200.0, 0.4, 5.3, 0.8), (1.0, 0.0, 7.1, 1.2)]):
+        lc = torch.randn((B, n, m, V), generator=gcpu) * 4
+        lu = lc + torch.randn((B, n, m, V), generator=gcpu)
+        q = torch.empty((B * n * m, V)).exponential_(1, generator=gcpu)
+        gum = -torch.log(-torch.log(torch.rand((B, n, m), generator=gcpu).clamp_min(1e-20)))
+        pred_t, masked_t = O.select_step(lc, lu, scale, temperature, q, gum, 8.2 * omp, torch.tensor(mask_len), masked_t, V)
+        a = _lib.MBSelectArgs()
+        pred = torch.empty_like(masked_d)
+        out = torch.empty_like(masked_d)
+        lc_d, lu_d, q_d, g_d = lc.cuda(), lu.cuda(), q.cuda(), gum.cuda()
+        a.logits_c, a.logits_u, a.q, a.gumbel = lc_d.data_ptr(), lu_d.data_ptr(), q_d.data_ptr(), g_d.data_ptr()
+        a.tokens_in, a.predicted, a.tokens_out = masked_d.data_ptr(), pred.data_ptr(), out.data_ptr()
+        a.scale, a.temperature, a.randomize_temperature, a.one_minus_progress, a.mask_len = scale, temperature, 8.2, omp, mask_len
+        a.B, a.n, a.splits, a.V, a.seq_stride, a.mask_token, a.seed, a.step = B, n, m, V, n, V, 0, i
+        _lib.check(_lib.lib().mb_select_step(gen._engine(), ctypes.byref(a), _lib.current_stream()))
+        torch.cuda.synchronize()
+        mism += int((pred.cpu() != pred_t).sum()) + int((out.cpu() != masked_t).sum())
+        total += 2 * pred_t.numel()
+        masked_d = out
+    print(f"select vs torch oracle V={V}: {total} compared values, {mism} mismatches")
+    assert mism == 0
+
+
+def test_noise_transforms_are_finite_at_the_extremes():
+    """Production-mode noise: the uniform built from a raw Philox word must lie strictly inside (0,1) for EVERY word --
+    r = 0xFFFFFFFF used to round to 1.0f, giving q = -log(1) = -0 (token unselectable or NaN) and a +inf Gumbel value."""
+    r = torch.tensor([0, 1, 0x1FF, 0x200, 0x7FFFFFFF, 0x80000000, 0xFFFFFE00, 0xFFFFFFFF], dtype=torch.int64)
+    r = torch.cat([r, torch.randint(0, 2 ** 32, (4096,), generator=torch.Generator().manual_seed(1))])
+    rd = torch.from_numpy(r.numpy().astype(np.uint32).view(np.int32)).cuda()
+    u, q, g = (torch.empty(r.numel(), device="cuda") for _ in range(3))
+    _lib.check(_lib.lib().mb_test_noise_transform(_p(rd), _p(u), _p(q), _p(g), r.numel(), _lib.current_stream()))
+    torch.cuda.synchronize()
+    u, q, g = u.cpu().double(), q.cpu().double(), g.cpu().double()
+    assert u.min().item() >= 2.0 ** -24 and u.max().item() <= 1.0 - 2.0 ** -24
+    assert torch.isfinite(q).all() and (q > 0).all() and torch.isfinite(g).all()
+    want_u = ((r >> 9).double() + 0.5) * 2.0 ** -23
+    assert torch.equal(u, want_u)
+    assert ((q + torch.log(want_u)).abs() <= 4e-7 * q.abs() + 1e-9).all()                  # Exp(1) = -log u to ~2 ulp, also next to u = 1
+    assert ((g + torch.log(-torch.log(want_u))).abs() <= 2e-6 * g.abs() + 2e-6).all()
+
+
 def test_select_rejects_aliasing_and_bad_vocab():
     _, _, _, gen = models(12)
     t = torch.zeros((1, 256, 2), dtype=torch.int64, device="cuda")
@@ -262,6 +352,86 @@ def test_decode_matches_reference_golden(golden_dir):
     # any-int / float token dtypes are accepted like the reference (`.long()`, lookup_free.py:108)
     assert torch.equal(tokenizer.decode_tokens(tokens.float()), img)
     assert torch.equal(tokenizer.decode_tokens(tokens.int()), img)
+
+
+def test_decode_14bit_matches_reference_golden(golden_dir):
+    """BASELINE configs[2] tokenizer (14-bit: conv_in 14 -> 512) against the reference's own decode."""
+    g = np.load(os.path.join(golden_dir, "decode_14bit.npz"))
+    _, _, tokenizer, _ = models(14)
+    img = tokenizer.decode_tokens(torch.from_numpy(g["tokens"].astype(np.int64)).cuda())
+    d0 = (img[0].cpu() - torch.from_numpy(g["image0"])).abs().max().item()
+    ds = (img[:, :, ::4, ::4].cpu() - torch.from_numpy(g["image_sub"])).abs().max().item()
+    print(f"decode 14bit: max abs pixel error {max(d0, ds):.3e}")
+    assert d0 <= PIXEL_MAX_ABS and ds <= PIXEL_MAX_ABS
+
+
+def test_sample_14bit_against_reference_run(golden_dir):
+    """BASELINE configs[2] model end to end against the reference's own sample() run (B=4, 8 steps, 14-bit, V = 128):
+    select on the reference's recorded logits (steps 0 and 5) -> its tokens, bit-exact; CUDA forward on its recorded step inputs
+    -> its logits within tolerance; decode of its final tokens -> its pixels within 1e-3; and the free-running CUDA sampler with the
+    reference's noise stream agrees with its first step except where bf16 logits flip an argmax."""
+    g = np.load(os.path.join(golden_dir, "sample_14bit.npz"))
+    _, kw, tokenizer, gen = models(14)
+    kw = dict(kw, num_steps=8)
+    B, steps = 4, 8
+    labels = torch.from_numpy(g["labels"])
+    torch.manual_seed(1234)
+    noise = [O.draw_step_noise(B, 256, 2, 128) for _ in range(steps)]
+    scale, temp, omp, mask_len = step_tables(steps, 512, softmax_temperature=kw["softmax_temperature"],
+                                             mask_schedule_strategy=kw["mask_schedule_strategy"], guidance_scale=kw["guidance_scale"],
+                                             guidance_annealing=kw["guidance_annealing"], scale_pow=kw["scale_pow"],
+                                             use_sampling_annealing=kw["use_sampling_annealing"])
+    drop = torch.cat([torch.zeros(B, dtype=torch.bool), torch.ones(B, dtype=torch.bool)]).cuda()
+    lab2 = torch.cat([labels, labels]).cuda()
+    for s in g["keep_steps"].tolist():
+        ref_logits = torch.from_numpy(g[f"logits_{s}"]).cuda()
+        tin = torch.from_numpy(g[f"tokens_in_{s}"].astype(np.int64)).cuda()
+        q, gum = noise[s]
+        pred, _ = select_step(gen, ref_logits[:B].contiguous(), ref_logits[B:].contiguous(), q.cuda(), gum.cuda(), tin, scale=scale[s],
+                              temperature=temp[s], rt=kw["randomize_temperature"], omp=omp[s], mask_len=mask_len[s], step=s)
+        ref_tok = torch.from_numpy(g["tokens"][s].astype(np.int64)).cuda()
+        assert torch.equal(pred, ref_tok), f"14-bit select differs from the reference at step {s}"
+        logits = gen(torch.cat([tin, tin]), lab2, drop)
+        d = (logits - ref_logits).abs()
+        print(f"14bit step {s}: logits max abs {d.max().item():.3e} mean abs {d.mean().item():.3e}")
+        assert d.max().item() <= LOGIT_MAX_ABS and d.mean().item() <= LOGIT_MEAN_ABS
+    from maskbit_b200 import combine_factorized_tokens
+    final = torch.from_numpy(g["tokens"][-1].astype(np.int64)).cuda()
+    img = tokenizer.decode_tokens(combine_factorized_tokens(final, 2 ** 14, 2))
+    e0 = (img[0].cpu() - torch.from_numpy(g["image0"])).abs().max().item()
+    es = (img[:, :, ::4, ::4].cpu() - torch.from_numpy(g["image_sub"])).abs().max().item()
+    print(f"14bit sample: decoded pixels max abs error {max(e0, es):.3e}")
+    assert e0 <= PIXEL_MAX_ABS and es <= PIXEL_MAX_ABS
+    torch.manual_seed(1234)
+    _, trace = sample(gen, tokenizer, num_samples=B, labels=labels, noise="reference_cpu", **kw)
+    agree = (trace[0] == torch.from_numpy(g["tokens"][0].astype(np.int64)).cuda()).float().mean().item()
+    print(f"14bit free-running step-0 token agreement with the reference: {agree:.4f}")
+    assert agree >= STEP0_AGREEMENT_MIN
+
+
+def test_forward_trained_like_checkpoint(golden_dir):
+    """A checkpoint with trained-like statistics (weights.trained_like_lfq_bert_state_dict: LayerNorm gains 0.1 .. 5 with outlier
+    channels, biases with a common offset and +-3 entries, wider projections -> logit range of tens): the bf16 pre-norm stream and
+    the folded LayerNorms against the reference's own fp32 logits (ADVICE r1 / VERDICT r1 weak #4).  The bar scales with the logit
+    range: the synthetic N(0, 0.02) checkpoints give |logit| < 1 and 3e-2 max error; here |logit| reaches 14."""
+    from maskbit_b200.weights import trained_like_lfq_bert_state_dict
+    g = np.load(os.path.join(golden_dir, "forward_trained_like_12bit.npz"))
+    cfg = load_config("maskbit_generator_12bit")
+    mlm = cfg.model.mlm_model
+    gen = LFQBert(img_size=256, hidden_dim=mlm.hidden_dim, codebook_size=4096, codebook_splits=2, depth=mlm.depth, heads=mlm.heads,
+                  mlp_dim=mlm.mlp_dim, dropout=0.0, use_prenorm=False, input_stride=16)
+    gen.load_state_dict(trained_like_lfq_bert_state_dict(seed=11, codebook_size=4096), strict=True)
+    gen = gen.to("cuda")
+    logits = gen(torch.from_numpy(g["tokens"].astype(np.int64)).cuda(), torch.from_numpy(g["labels"]).cuda(),
+                 torch.from_numpy(g["drop"]).cuda()).cpu()
+    ref = torch.from_numpy(g["logits"])
+    d = (logits - ref).abs()
+    rng = ref.abs().max().item()
+    # what matters downstream is the softmax: compare probabilities too
+    dp = (torch.softmax(logits, -1) - torch.softmax(ref, -1)).abs()
+    print(f"trained-like forward: logit range {rng:.1f}, max abs {d.max().item():.3e}, mean abs {d.mean().item():.3e}, "
+          f"relative to range {d.max().item() / rng:.3e}; softmax max abs {dp.max().item():.3e}")
+    assert d.max().item() <= TRAINED_LIKE_MAX_REL * rng and d.mean().item() <= TRAINED_LIKE_MEAN_REL * rng
 
 
 def test_decode_batch_chunking_and_latents():
@@ -364,7 +534,7 @@ def test_teacher_forced_chain(golden_dir):
         assert torch.equal(pred, ref_tok)
         agree = (pred_own == ref_tok).float().mean().item()
         print(f"step {i}: logits max abs {d.max().item():.3e}; token agreement with own logits {agree:.4f}")
-        assert agree >= 0.90
+        assert agree >= TEACHER_FORCED_AGREEMENT_MIN
 
 
 # ------------------------------------------------------------------------------------------------ P5 sampler
@@ -395,7 +565,7 @@ def test_sample_config1_structure(golden_dir):
     ref0 = torch.from_numpy(g["tokens"][0].astype(np.int64)).cuda()
     agree = (trace[0] == ref0).float().mean().item()
     print(f"config1 step-0 token agreement with the reference: {agree:.4f}")
-    assert agree >= 0.95
+    assert agree >= STEP0_AGREEMENT_MIN
     ks = _k_table(8, kw)
     for i in range(7):
         kept = (trace[i + 1] == trace[i]).reshape(4, -1).sum(1)   # tokens fixed after step i stay fixed
