@@ -149,6 +149,25 @@ typedef struct mb_sample_args {
  * `stream` at entry and exit (ordering seen from `stream` is unchanged); MASKBIT_B200_GRAPH_MAX_BATCH=0 disables it. */
 int mb_sample(mb_handle* h, const mb_sample_args* a, mb_stream stream);
 
+/* ---- forward half of the generator's training step (reference scripts/train_maskbit.py:362-380; no backward) ----
+ * Stateless: device pointers in, device pointers out, caller's stream.
+ *
+ * mb_split_tokens   modeling/modules/factorization.py:27-46: tokens int64 [n] -> out int64 [n, splits],
+ *                   out[i, g] = (tokens[i] >> (g * bits_per_split)) & (2^bits_per_split - 1)
+ * mb_mask_tokens    modeling/modules/masking.py:7-38 given the random draws: u fp32 [B, slots] uniform [0,1) per slot and
+ *                   val_to_mask fp32 [B] per sample (the host mirror maskbit_b200.masking.get_mask_tokens computes it with the
+ *                   reference's torch ops and draws u in the reference's order); masked = u < val ? mask_token : token,
+ *                   mask uint8 [B, slots] = the predicate
+ * mb_mlm_loss       modeling/modules/losses.py:289-339 MLMLoss.forward: logits fp32 [rows, V] (rows = B*n*m), targets int64 [rows],
+ *                   masks uint8 [rows] -> out4 fp32 {mlm_loss, correct_tokens, masked_token_loss, masked_correct_tokens};
+ *                   scratch: mb_mlm_loss_scratch_bytes() bytes of device memory.  Deterministic (fixed summation order). */
+int mb_split_tokens(const int64_t* tokens, int64_t n, int splits, int bits_per_split, int64_t* out, mb_stream stream);
+int mb_mask_tokens(const int64_t* tokens, const float* u, const float* val_to_mask, int64_t mask_token, int64_t* masked,
+                   uint8_t* mask, int B, int slots, mb_stream stream);
+int mb_mlm_loss_scratch_bytes(void);
+int mb_mlm_loss(const float* logits, const int64_t* targets, const uint8_t* masks, int64_t rows, int V, int splits,
+                float label_smoothing, int sum_splits, void* scratch, float* out4, mb_stream stream);
+
 /* Number of kernels the library has launched on this handle since creation (bench.py "gpu_launches"). */
 int64_t mb_launch_count(mb_handle* h);
 

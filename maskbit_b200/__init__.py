@@ -8,7 +8,8 @@ from .bert import Bert, LFQBert  # noqa: F401
 from .conv_vqgan import ConvVQModel  # noqa: F401
 from .sampling import sample  # noqa: F401
 from .factorization import combine_factorized_tokens, split_factorized_tokens  # noqa: F401
-from .masking import get_masking_ratio  # noqa: F401
+from .masking import get_mask_tokens, get_masking_ratio  # noqa: F401
+from .losses import MLMLoss  # noqa: F401
 
 
 def build_models(config, device="cuda", generator_path=None, tokenizer_path=None):

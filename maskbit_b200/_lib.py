@@ -57,6 +57,10 @@ SYMBOLS = {
     "mb_combine_tokens": (_I, [_P, _P, _I, _P, _P]),
     "mb_postprocess_u8": (_I, [_P, _P, _I, _P, _P]),
     "mb_sample": (_I, [_P, ctypes.POINTER(MBSampleArgs), _P]),
+    "mb_split_tokens": (_I, [_P, ctypes.c_int64, _I, _I, _P, _P]),
+    "mb_mask_tokens": (_I, [_P, _P, _P, ctypes.c_int64, _P, _P, _I, _I, _P]),
+    "mb_mlm_loss_scratch_bytes": (_I, []),
+    "mb_mlm_loss": (_I, [_P, _P, _P, ctypes.c_int64, _I, _I, _F, _I, _P, _P, _P]),
     "mb_launch_count": (ctypes.c_int64, [_P]),
     "mb_profile_enable": (_I, [_P, _I]),
     "mb_profile_read": (_I, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64), _I]),

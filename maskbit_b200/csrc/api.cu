@@ -21,6 +21,7 @@
 #include "encoder.cuh"
 #include "gemm_tcgen05.cuh"
 #include "select.cuh"
+#include "train_fwd.cuh"
 
 using namespace mb;
 
@@ -137,6 +138,29 @@ fold_ln_kernel(const float* __restrict__ w, const float* __restrict__ gamma, con
 __global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = a[i] + b[i];
+}
+// v[i] -= mean(v): one block.  The residual epilogues store y = acc + (bias + beta_res) + ...; every consumer of y is a LayerNorm,
+// which is invariant to adding a constant to the whole row, so the common offset of the folded bias vector carries no
+// information -- but it costs bf16 resolution of the stored stream (delta = |row mean| * 2^-8) when it is large against the
+// row's spread, as trained LayerNorm biases can be.  Removing it at load time is free.
+#ifndef MB_CENTER_RESIDUAL_BIAS
+#define MB_CENTER_RESIDUAL_BIAS 1
+#endif
+__global__ void __launch_bounds__(1024) center_vec_kernel(float* __restrict__ v, int n) {
+    __shared__ float red[32];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) red[0] = t / (float)n;
+    }
+    __syncthreads();
+    const float m = red[0];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v[i] -= m;
 }
 // conv weight fp32 [Cout][Cin][kh][kw] -> split bf16 hi/lo [Cout][tap*Cin + c]
 __global__ void pack_conv_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
@@ -452,6 +476,7 @@ static int make_linear_res(mb_handle* h, const std::string& wname, const std::st
     L->v2 = ln_res.g;
     f32_to_bf16_kernel<<<(unsigned)(((size_t)N * K + 255) / 256), 256>>>(w.ptr, L->w, (size_t)N * K);
     add_vec_kernel<<<(N + 255) / 256, 256>>>(b.ptr, ln_res.b, L->b, N);
+    if (MB_CENTER_RESIDUAL_BIAS) center_vec_kernel<<<1, 1024>>>(L->b, N);
     CU_TRY(cudaGetLastError());
     MB_TRY(make_tmap_bf16(&L->tm, L->w, N, K, L->BN));
     MB_TRY(make_tmap_bf16(&L->tm_half, L->w, N, K, 128));
@@ -839,7 +864,7 @@ static int run_attention(mb_handle* h, const CUtensorMap& tm_big, const CUtensor
         AttnTcParams p;
         p.out = out; p.n_items = n_seq * H; p.H = H; p.D = D; p.sl2 = sl2; p.trace = g_attn_trace;
         const int grid = p.n_items < num_sms ? p.n_items : num_sms;
-        attention_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM_BYTES, st>>>(tm_big, tm_row, tm_out, p);
+        attention_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM_BYTES, st>>>(tm_big, tm_row, p);
     } else {
         attention_kernel<<<n_seq * H, ATT_THREADS, 2 * ATT_MAXS * ATT_LDS * 2, st>>>(qkv, out, S, D, H, sl2);
     }
@@ -1285,6 +1310,37 @@ extern "C" int mb_sample(mb_handle* h, const mb_sample_args* a, mb_stream stream
         CU_TRY(cudaEventRecord(h->ev_out, st));
         CU_TRY(cudaStreamWaitEvent(caller, h->ev_out, 0));
     }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ training step, forward half
+extern "C" int mb_split_tokens(const int64_t* tokens, int64_t n, int splits, int bits_per_split, int64_t* out, mb_stream stream) {
+    if (!tokens || !out || n <= 0 || splits < 1 || bits_per_split < 1 || splits * bits_per_split > 62)
+        return fail(MB_ERR_INVALID, "mb_split_tokens: bad argument");
+    split_tokens_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(tokens, out, (size_t)n, splits, bits_per_split);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+extern "C" int mb_mask_tokens(const int64_t* tokens, const float* u, const float* val_to_mask, int64_t mask_token, int64_t* masked,
+                              uint8_t* mask, int B, int slots, mb_stream stream) {
+    if (!tokens || !u || !val_to_mask || !masked || !mask || B <= 0 || slots <= 0) return fail(MB_ERR_INVALID, "mb_mask_tokens: bad argument");
+    const size_t n = (size_t)B * slots;
+    mask_tokens_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(tokens, u, val_to_mask, mask_token, masked, mask, B, slots);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+extern "C" int mb_mlm_loss_scratch_bytes(void) { return MLM_BLOCKS * MLM_PARTIALS * (int)sizeof(double); }
+extern "C" int mb_mlm_loss(const float* logits, const int64_t* targets, const uint8_t* masks, int64_t rows, int V, int splits,
+                           float label_smoothing, int sum_splits, void* scratch, float* out4, mb_stream stream) {
+    if (!logits || !targets || !masks || !scratch || !out4 || rows <= 0 || V <= 0 || splits < 1)
+        return fail(MB_ERR_INVALID, "mb_mlm_loss: bad argument");
+    const long long want = (rows + 7) / 8;
+    const int blocks = want < MLM_BLOCKS ? (int)want : MLM_BLOCKS;
+    mlm_loss_partial_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(logits, targets, masks, rows, V, static_cast<double*>(scratch));
+    CU_TRY(cudaGetLastError());
+    mlm_loss_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(static_cast<const double*>(scratch), blocks, rows, splits, label_smoothing,
+                                                             sum_splits, out4);
+    CU_TRY(cudaGetLastError());
     return 0;
 }
 

@@ -23,7 +23,7 @@
 // 257 = 2*128 + 1: tensor tiles cover the 256x256 block exactly; the odd row and column never touch a padded tcgen05 tile.
 //
 // Input  qkv  bf16 [rows, 3*D] through two TMA maps (box 64x256 and box 64x16); head h at columns h*64 of each third
-// Output out  bf16 [n_seq*257, D] (rows 0..255 of every sequence through a TMA map with box 64x32, row 256 by direct stores)
+// Output out  bf16 [n_seq*257, D] (one 128-byte row segment per thread, 256-bit stores)
 #pragma once
 #include "attention.cuh"   // ldsm_x4, ldsm_x4_t, mma_bf16_16816
 #include "ptx.cuh"
@@ -125,8 +125,7 @@ struct AttnTcParams {
 };
 
 __global__ void __launch_bounds__(ATC_THREADS, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant__ CUtensorMap tm_row,
-                    const __grid_constant__ CUtensorMap tm_out, AttnTcParams p) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_constant__ CUtensorMap tm_row, AttnTcParams p) {
     constexpr int S = 257;
     extern __shared__ uint8_t atc_smem_raw[];
     const uint32_t raw = smem_u32(atc_smem_raw);
@@ -134,20 +133,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
     float* scls = reinterpret_cast<float*>(base + 2 * ATC_STAGE_BYTES);              // [2 stages][256 keys]
     __nv_bfloat16* pcls = reinterpret_cast<__nv_bfloat16*>(base + 2 * ATC_STAGE_BYTES + ATC_SCLS_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + 2 * ATC_STAGE_BYTES + ATC_SCLS_BYTES + ATC_PCLS_BYTES);
-    uint64_t* full = bars;           // [2] TMA landed
-    uint64_t* empty = bars + 2;      // [2] stage consumed (2 MMA issuers' commits + 8 softmax warps + class warp)
-    uint64_t* s_full = bars + 4;     // [2] S_t complete in TMEM
-    uint64_t* p_full = bars + 6;     // [2] P_t written to TMEM (4 warps)
-    uint64_t* o_full = bars + 8;     // [2] O_t complete
-    uint64_t* t_free = bars + 10;    // [2] TMEM region t drained by the epilogue (4 warps)
-    uint64_t* scls_ready = bars + 12;// [2] scls[stage] written by the 8 softmax warps
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    // Each stage is two independently recycled halves: Q | K | class rows of Q, K (needed until S and the class scores are done,
+    // early in an item) and V | class row of V (needed until P V is done, at its end).  With one barrier pair per stage the next
+    // item's load could only start when the LATER warpgroup had finished the previous item, and arrived ~2 k clk after the
+    // earlier warpgroup wanted it (profiles/r02c_attn_trace.txt).
+    uint64_t* fullqk = bars;         // [2] Q, K (+ class rows) landed
+    uint64_t* fullv = bars + 2;      // [2] V (+ class row) landed
+    uint64_t* emptyqk = bars + 4;    // [2] consumed: 2 S commits + 8 softmax warps (class pass) + class warp
+    uint64_t* emptyv = bars + 6;     // [2] consumed: 2 P V commits + 8 softmax warps (epilogue) + class warp
+    uint64_t* s_full = bars + 8;     // [2] S_t complete in TMEM
+    uint64_t* p_full = bars + 10;    // [2] P_t written to TMEM (4 warps)
+    uint64_t* o_full = bars + 12;    // [2] O_t complete
+    uint64_t* t_free = bars + 14;    // [2] TMEM region t drained by the epilogue (4 warps)
+    uint64_t* scls_ready = bars + 16;// [2] scls[stage] written by the 8 softmax warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_big); tma_prefetch_desc(&tm_row); tma_prefetch_desc(&tm_out); }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_big); tma_prefetch_desc(&tm_row); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&full[s], 1); mbar_init(&empty[s], 11);
+            mbar_init(&fullqk[s], 1); mbar_init(&fullv[s], 1); mbar_init(&emptyqk[s], 11); mbar_init(&emptyv[s], 11);
             mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 4); mbar_init(&o_full[s], 1); mbar_init(&t_free[s], 4);
             mbar_init(&scls_ready[s], 8);
         }
@@ -171,15 +176,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
                 const int seq = item / p.H, head = item - seq * p.H;
                 const int row0 = seq * S, col = head * 64;
                 uint8_t* sb = base + st * ATC_STAGE_BYTES;
-                mbar_wait(&empty[st], ph ^ 1);
+                // (the V half of a slot is released before the Q/K half of the other slot: waiting in this order never holds back
+                //  a load whose buffer is already free)
+                mbar_wait(&emptyqk[st], ph ^ 1);
                 ATC_EV(0, 0, it);
-                mbar_arrive_expect_tx(&full[st], ATC_STAGE_BYTES);
-                tma_load_2d(sb + ATC_TILE_BYTES, &tm_big, &full[st], p.D + col, row0);                   // K rows 0..255
-                tma_load_2d(sb, &tm_big, &full[st], col, row0);                                          // Q
-                tma_load_2d(sb + 3 * ATC_TILE_BYTES, &tm_row, &full[st], col, row0 + 256);               // Q[256..]
-                tma_load_2d(sb + 3 * ATC_TILE_BYTES + ATC_ROW_BYTES, &tm_row, &full[st], p.D + col, row0 + 256);      // K[256..]
-                tma_load_2d(sb + 2 * ATC_TILE_BYTES, &tm_big, &full[st], 2 * p.D + col, row0);           // V
-                tma_load_2d(sb + 3 * ATC_TILE_BYTES + 2 * ATC_ROW_BYTES, &tm_row, &full[st], 2 * p.D + col, row0 + 256);  // V[256..]
+                mbar_arrive_expect_tx(&fullqk[st], 2 * ATC_TILE_BYTES + 2 * ATC_ROW_BYTES);
+                tma_load_2d(sb + ATC_TILE_BYTES, &tm_big, &fullqk[st], p.D + col, row0);                 // K rows 0..255
+                tma_load_2d(sb, &tm_big, &fullqk[st], col, row0);                                        // Q
+                tma_load_2d(sb + 3 * ATC_TILE_BYTES, &tm_row, &fullqk[st], col, row0 + 256);             // Q[256..]
+                tma_load_2d(sb + 3 * ATC_TILE_BYTES + ATC_ROW_BYTES, &tm_row, &fullqk[st], p.D + col, row0 + 256);    // K[256..]
+                mbar_wait(&emptyv[st], ph ^ 1);
+                mbar_arrive_expect_tx(&fullv[st], ATC_TILE_BYTES + ATC_ROW_BYTES);
+                tma_load_2d(sb + 2 * ATC_TILE_BYTES, &tm_big, &fullv[st], 2 * p.D + col, row0);          // V
+                tma_load_2d(sb + 3 * ATC_TILE_BYTES + 2 * ATC_ROW_BYTES, &tm_row, &fullv[st], 2 * p.D + col, row0 + 256);  // V[256..]
             }
         }
     } else if (warp == 1 || warp == 2) {
@@ -191,7 +200,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
             for (int it = 0; it < n_local; ++it) {
                 const int st = it & 1;
                 const uint32_t sq = smem0 + st * ATC_STAGE_BYTES, sk = sq + ATC_TILE_BYTES, sv = sk + ATC_TILE_BYTES;
-                mbar_wait(&full[st], (it >> 1) & 1);
+                mbar_wait(&fullqk[st], (it >> 1) & 1);
                 mbar_wait(&t_free[t], (it & 1) ^ 1);
                 tc_fence_after();
                 {                                                               // S_t = Q_t K^T
@@ -199,16 +208,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
 #pragma unroll
                     for (int k = 0; k < 4; ++k) umma_f16(tr, a + 2 * k, b + 2 * k, idesc_s, k != 0);
                     umma_commit(&s_full[t]);
+                    umma_commit(&emptyqk[st]);                                  // this tile's S MMAs have read Q and K
                     ATC_EV(1, t, it);
                 }
                 mbar_wait(&p_full[t], it & 1);
+                mbar_wait(&fullv[st], (it >> 1) & 1);
                 tc_fence_after();
                 {                                                               // O_t = P_t V
                     const uint64_t b = make_sdesc_mn128(sv);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) umma_f16_ts(tr + 128, tr + 8 * j, b + (uint64_t)(j * 128), idesc_o, j != 0);
                     umma_commit(&o_full[t]);
-                    umma_commit(&empty[st]);                                    // this tile's MMAs have read the stage
+                    umma_commit(&emptyv[st]);                                   // this tile's P V MMAs have read V
                     ATC_EV(1, 2 + t, it);
                 }
             }
@@ -222,7 +233,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
             const int seq = item / p.H, head = item - seq * p.H;
             const uint32_t sq = smem0 + st * ATC_STAGE_BYTES, sv = sq + 2 * ATC_TILE_BYTES;
             const uint32_t qc = sq + 3 * ATC_TILE_BYTES, kc = qc + ATC_ROW_BYTES, vc = kc + ATC_ROW_BYTES;
-            mbar_wait(&full[st], ph);
+            mbar_wait(&fullqk[st], ph);
             if (lane == 0) ATC_EV(2, 0, it);
             // its score against its own key: lane l holds dims 2l, 2l+1
             const uint32_t qw = lds32(qc + lane * 4), kw = lds32(kc + lane * 4);
@@ -235,6 +246,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
             float mx = sd;
 #pragma unroll
             for (int i = 0; i < 8; ++i) { sc[i] = scls[st * 256 + lane + 32 * i]; mx = fmaxf(mx, sc[i]); }
+            // Only now hand the Q/K half back: the softmax warps refill scls[st] (and re-arrive on scls_ready[st]) as soon as the
+            // NEXT item using this slot has landed, which must not happen before this warp has read the current scores.
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&emptyqk[st]);
 #pragma unroll
             for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             const float nms = -mx * p.sl2;
@@ -250,6 +265,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
             const float e256 = fast_exp2(fmaf(sd, p.sl2, nms));
             if (lane < 16) pcls[256 + lane] = __float2bfloat16_rn(lane == 0 ? e256 : 0.f);   // keys 257.. do not exist
             __syncwarp();
+            mbar_wait(&fullv[st], ph);
             // O^T[d][0] = sum_key V^T[d][key] p[key]: 4 d-tiles x 17 key-tiles of m16n8k16 (tile 16 = keys 256..271 from the
             // class-row box); A = V^T by ldmatrix.trans of the swizzled V tile, B = p in column n = 0
             float o[4][4];
@@ -278,7 +294,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
                 }
             }
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&empty[st]); ATC_EV(2, 1, it); }
+            if (lane == 0) { mbar_arrive(&emptyv[st]); ATC_EV(2, 1, it); }
         }
     } else if (warp >= 4) {  // ------------------------------------------------------------ softmax + epilogue
         const int t = (warp - 4) >> 2, quarter = warp & 3;
@@ -287,54 +303,54 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
 #if ATC_PINGPONG
         if (t == 1) named_bar_arrive(1, 256);                          // warpgroup 0 takes the first turn in pass 2
 #endif
+        // ---- the 257th column and row for this warp's 32 query rows / 32 keys (rows base .. base+31 of the Q and K tiles of local
+        // item `j`): m16n8k16 tiles with the class-token vector as the single live column of B.  Returns s256 of this thread's row.
+        // Runs one item AHEAD (for item j+1 while item j's P V MMAs are in flight): on the warpgroup's serial chain between two
+        // items it cost ~1.8 k clk per item (profiles/r02d_attn_trace.txt).
+        auto class_pass = [&](uint32_t j) -> float {
+            const int st = j & 1;
+            const uint32_t sq = smem0 + st * ATC_STAGE_BYTES, sk = sq + ATC_TILE_BYTES;
+            const uint32_t qc = sq + 3 * ATC_TILE_BYTES, kc = qc + ATC_ROW_BYTES;
+            mbar_wait(&fullqk[st], (j >> 1) & 1);
+            const int g = lane >> 2, t4 = lane & 3, base_row = row - lane;
+            float ccol[2][4], crow[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { ccol[mt][i] = 0.f; crow[mt][i] = 0.f; }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                // B fragments: b0 = dims 16kk+2t4,+1 ; b1 = dims 16kk+8+2t4,+1 (column n = g = 0 only)
+                const uint32_t kb0 = g == 0 ? lds32(kc + (kk * 8 + t4) * 4) : 0u, kb1 = g == 0 ? lds32(kc + (kk * 8 + 4 + t4) * 4) : 0u;
+                const uint32_t qb0 = g == 0 ? lds32(qc + (kk * 8 + t4) * 4) : 0u, qb1 = g == 0 ? lds32(qc + (kk * 8 + 4 + t4) * 4) : 0u;
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const int r = base_row + mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                    uint32_t a[4];
+                    ldsm_x4(a, sw128(sq, r, kk * 2 + (lane >> 4)));
+                    mma_bf16_16816(ccol[mt], a, kb0, kb1);                 // Q[r] . K[256]
+                    ldsm_x4(a, sw128(sk, r, kk * 2 + (lane >> 4)));
+                    mma_bf16_16816(crow[mt], a, qb0, qb1);                 // K[r] . Q[256]
+                }
+            }
+            if (t4 == 0) {
+                float* dst = scls + st * 256 + base_row + g;
+                dst[0] = crow[0][0]; dst[8] = crow[0][2]; dst[16] = crow[1][0]; dst[24] = crow[1][2];
+            }
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&scls_ready[st]); mbar_arrive(&emptyqk[st]); }
+            // row base + lane = m-tile lane >> 4, fragment row lane & 15: held by lane 4 * (lane & 7) as c[0] (rows 0..7) or c[2]
+            const int src = (lane & 7) * 4;
+            const float v00 = __shfl_sync(0xffffffffu, ccol[0][0], src), v02 = __shfl_sync(0xffffffffu, ccol[0][2], src);
+            const float v10 = __shfl_sync(0xffffffffu, ccol[1][0], src), v12 = __shfl_sync(0xffffffffu, ccol[1][2], src);
+            return (lane & 16) ? ((lane & 8) ? v12 : v10) : ((lane & 8) ? v02 : v00);
+        };
+        float s256 = n_local > 0 ? class_pass(0) : 0.f;
         uint32_t it = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
             const int st = it & 1; const uint32_t ph = (it >> 1) & 1, ip = it & 1;
             const int seq = item / p.H, head = item - seq * p.H;
-            const uint32_t sq = smem0 + st * ATC_STAGE_BYTES, sk = sq + ATC_TILE_BYTES;
-            const uint32_t qc = sq + 3 * ATC_TILE_BYTES, kc = qc + ATC_ROW_BYTES, vc = kc + ATC_ROW_BYTES;
-            // ---- the 257th column and row for this warp's 32 query rows / 32 keys (rows base .. base+31 of the Q and K tiles):
-            // m16n8k16 tiles with the class-token vector as the single live column of B
-            float s256;
-            {
-                mbar_wait(&full[st], ph);
-                const int g = lane >> 2, t4 = lane & 3, base_row = row - lane;
-                float ccol[2][4], crow[2][4];
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { ccol[mt][i] = 0.f; crow[mt][i] = 0.f; }
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    // B fragments: b0 = dims 16kk+2t4,+1 ; b1 = dims 16kk+8+2t4,+1 (column n = g = 0 only)
-                    const uint32_t kb0 = g == 0 ? lds32(kc + (kk * 8 + t4) * 4) : 0u, kb1 = g == 0 ? lds32(kc + (kk * 8 + 4 + t4) * 4) : 0u;
-                    const uint32_t qb0 = g == 0 ? lds32(qc + (kk * 8 + t4) * 4) : 0u, qb1 = g == 0 ? lds32(qc + (kk * 8 + 4 + t4) * 4) : 0u;
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
-                        const int r = base_row + mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-                        uint32_t a[4];
-                        ldsm_x4(a, sw128(sq, r, kk * 2 + (lane >> 4)));
-                        mma_bf16_16816(ccol[mt], a, kb0, kb1);                 // Q[r] . K[256]
-                        ldsm_x4(a, sw128(sk, r, kk * 2 + (lane >> 4)));
-                        mma_bf16_16816(crow[mt], a, qb0, qb1);                 // K[r] . Q[256]
-                    }
-                }
-                if (t4 == 0) {
-                    float* dst = scls + st * 256 + base_row + g;
-                    dst[0] = crow[0][0]; dst[8] = crow[0][2]; dst[16] = crow[1][0]; dst[24] = crow[1][2];
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&scls_ready[st]);
-                // row base + lane = m-tile lane >> 4, fragment row lane & 15: held by lane 4 * (lane & 7) as c[0] (rows 0..7) or c[2]
-                const int src = (lane & 7) * 4;
-                const float v00 = __shfl_sync(0xffffffffu, ccol[0][0], src), v02 = __shfl_sync(0xffffffffu, ccol[0][2], src);
-                const float v10 = __shfl_sync(0xffffffffu, ccol[1][0], src), v12 = __shfl_sync(0xffffffffu, ccol[1][2], src);
-                s256 = (lane & 16) ? ((lane & 8) ? v12 : v10) : ((lane & 8) ? v02 : v00);
-            }
-            // The previous item's output store has had the class pass above to read its staging rows: only now release that stage
-            // to the producer (waiting for the read right after the store put ~1 k clk on this warpgroup's serial chain).
-            if (it > 0 && elect_one()) { tma_store_wait_read<0>(); mbar_arrive(&empty[st ^ 1]); }
-            __syncwarp();
+            const uint32_t vc = smem0 + st * ATC_STAGE_BYTES + 3 * ATC_TILE_BYTES + 2 * ATC_ROW_BYTES;
             mbar_wait(&s_full[t], ip);
             tc_fence_after();
             if (quarter == 0 && lane == 0) ATC_EV(3 + t, 0, it);
@@ -391,13 +407,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[t]);
             if (quarter == 0 && lane == 0) ATC_EV(3 + t, 2, it);
+            const float s256_next = (int)it + 1 < n_local ? class_pass(it + 1) : 0.f;   // while this item's P V MMAs run
             // epilogue: (O + p256 * V[256]) / (l + p256) -> bf16 row
             const float e256 = fast_exp2(fmaf(s256, p.sl2, nms));
             const float inv = 1.0f / (sum0 + sum1 + e256);
             const float ei = e256 * inv;
-            // Output staging: this warp's 32 rows of the Q tile (S_t is complete, and the only other reader of these rows was this
-            // warp's own class-column pass above), 128-byte rows with the 128B swizzle, then ONE TMA store of the 32 x 64 box.
-            uint8_t* stg = base + st * ATC_STAGE_BYTES + t * (128 * 128) + quarter * 4096;
+            // Output: each thread owns one 128-byte row of the head's 64 columns and writes it with four 256-bit stores (whole
+            // 32-byte sectors): no shared-memory staging, so nothing of the stage outlives the item.
+            mbar_wait(&fullv[st], ph);                                 // (long complete) makes the TMA-written V[256] row visible
+            uint32_t vcw[32];                                          // V[256][0..63] as bf16 pairs, same for every row
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 vv = lds128(vc + c * 16);
+                vcw[4 * c] = vv.x; vcw[4 * c + 1] = vv.y; vcw[4 * c + 2] = vv.z; vcw[4 * c + 3] = vv.w;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&emptyv[st]);                   // this warp's last read of the stage
             mbar_wait(&o_full[t], ip);
             tc_fence_after();
             if (quarter == 0 && lane == 0) ATC_EV(3 + t, 3, it);
@@ -407,34 +432,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
             tc_fence_before();                                         // O is in registers: the TMEM tile can take the next item's S now
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_free[t]);
+            __nv_bfloat16* orow = p.out + ((size_t)seq * S + row) * p.D + head * 64;
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
                 const uint32_t (&vo)[32] = hh ? vb : va;
+                uint32_t o[16];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const uint4 vv = lds128(vc + (hh * 4 + c) * 16);
-                    const uint32_t w[4] = {vv.x, vv.y, vv.z, vv.w};
-                    uint32_t o[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float a = fmaf(__uint_as_float(vo[c * 8 + 2 * j]), inv, bf_lo(w[j]) * ei);
-                        const float b = fmaf(__uint_as_float(vo[c * 8 + 2 * j + 1]), inv, bf_hi(w[j]) * ei);
-                        o[j] = pack2_bf16(a, b);
-                    }
-                    *reinterpret_cast<uint4*>(stg + lane * 128 + (((hh * 4 + c) ^ (lane & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t w = vcw[hh * 16 + j];
+                    const float a = fmaf(__uint_as_float(vo[2 * j]), inv, bf_lo(w) * ei);
+                    const float b = fmaf(__uint_as_float(vo[2 * j + 1]), inv, bf_hi(w) * ei);
+                    o[j] = pack2_bf16(a, b);
                 }
+                st_global_v8(orow + hh * 32, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+                st_global_v8(orow + hh * 32 + 16, o[8], o[9], o[10], o[11], o[12], o[13], o[14], o[15]);
             }
-            fence_async_proxy();
-            __syncwarp();
-            if (elect_one()) {
-                tma_store_2d(&tm_out, stg, head * 64, seq * S + t * 128 + quarter * 32);
-                tma_store_commit();                                    // (the stage is released in the next iteration, above)
-            }
-            __syncwarp();
             if (quarter == 0 && lane == 0) ATC_EV(3 + t, 4, it);
+            s256 = s256_next;
         }
     }
-    if (warp >= 4 && elect_one()) tma_store_wait_all<0>();   // the same elected lane that committed the bulk stores
     __syncwarp();
     tc_fence_before();
     __syncthreads();

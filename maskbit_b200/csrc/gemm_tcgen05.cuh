@@ -192,12 +192,6 @@ __device__ __forceinline__ void gelu_poly2(float& x0, float& x1) {
     fmul2(x0, x1, x0, x1, __saturatef(fmaf(x0, q0, 0.5f)), __saturatef(fmaf(x1, q1, 0.5f)));     // x * Phi(x)
 }
 
-__device__ __forceinline__ void st_global_v8(void* ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
-                                             uint32_t g, uint32_t h) {
-    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                 ::"l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
-}
-
 // mean and rstd of a row from its LN_PARTIALS partial sums
 __device__ __forceinline__ void ln_row_stats(const float2* __restrict__ st, float inv_d, float eps, float& mean, float& rstd) {
     const float4* q = reinterpret_cast<const float4*>(st);

@@ -17,6 +17,14 @@ def combine_factorized_tokens(tokens: torch.Tensor, codebook_size: int, splits: 
 
 
 def split_factorized_tokens(tokens: torch.Tensor, codebook_size: int, splits: int) -> torch.Tensor:
+    """[B, n] full index -> [B, n, splits] group tokens (factorization.py:27-46), mb_split_tokens on CUDA tensors."""
     bit_shift = int(math.log2(codebook_size)) // splits
-    bit_mask = (1 << bit_shift) - 1
-    return torch.stack([(tokens & (bit_mask << (i * bit_shift))) >> (i * bit_shift) for i in range(splits)], dim=2)
+    if tokens.device.type != "cuda":
+        raise _lib.MaskbitError("split_factorized_tokens runs on a CUDA device; there is no CPU fallback")
+    tok = tokens.to(torch.int64).contiguous()
+    out = torch.empty(tuple(tok.shape) + (splits,), dtype=torch.int64, device=tok.device)
+    if tok.numel():
+        with torch.cuda.device(tok.device):
+            _lib.check(_lib.lib().mb_split_tokens(ctypes.c_void_p(tok.data_ptr()), tok.numel(), splits, bit_shift,
+                                                  ctypes.c_void_p(out.data_ptr()), _lib.current_stream()))
+    return out

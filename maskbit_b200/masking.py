@@ -51,3 +51,45 @@ def step_tables(num_steps, num_maskable, *, softmax_temperature, mask_schedule_s
         ratio = get_masking_ratio(progress, mode=mask_schedule_strategy)
         mask_len.append(float(torch.floor(ratio * num_maskable)))
     return scale, temp, omp, mask_len
+
+
+def get_mask_tokens(tokens, mask_token, mode="arccos", min_masking_ratio=0.0, *, noise="reference_cpu", generator=None):
+    """Drop-in mirror of modeling/modules/masking.py:7-38 (training-time random masking): returns (masked_tokens, mask).
+
+    The per-sample ratio and the per-slot uniforms are drawn exactly like the reference draws them -- on the CPU, from torch's
+    default generator (or `generator`), first ``rand(B)`` then ``rand(tokens.size())`` -- so the same seed masks the same slots;
+    the compare-and-replace runs on the device (mb_mask_tokens).  ``noise="device"`` draws the per-slot uniforms with torch's CUDA
+    generator instead (no host->device copy; not reproducible against the reference).  ``mask`` is returned on the tokens' device
+    (the reference leaves it on the CPU, masking.py:35)."""
+    import ctypes
+
+    from . import _lib
+    if tokens.device.type != "cuda":
+        raise _lib.MaskbitError("get_mask_tokens runs on a CUDA device (tokens must be a CUDA tensor); there is no CPU fallback")
+    b = tokens.size(0)
+    r = torch.rand(b, generator=generator) * (1 - min_masking_ratio)
+    if mode == "linear":
+        val_to_mask = 1 - r
+    elif mode == "square":
+        val_to_mask = 1 - (r ** 2)
+    elif mode == "cosine":
+        val_to_mask = torch.cos(r * math.pi * 0.5)
+    elif mode == "arccos":
+        val_to_mask = torch.acos(r) / (math.pi * 0.5)
+    else:
+        raise ValueError("Invalid mode. Choose between 'linear','square', 'cosine', 'arccos'.")
+    if noise == "reference_cpu":
+        u = torch.rand(tokens.size(), generator=generator).to(tokens.device, non_blocking=True)
+    elif noise == "device":
+        u = torch.rand(tokens.size(), device=tokens.device)
+    else:
+        raise ValueError("noise must be 'reference_cpu' or 'device'")
+    tok = tokens.detach().to(torch.int64).contiguous()
+    val = val_to_mask.to(device=tokens.device, dtype=torch.float32).contiguous()
+    masked = torch.empty_like(tok)
+    mask = torch.empty(tok.shape, dtype=torch.bool, device=tok.device)
+    with torch.cuda.device(tok.device):
+        _lib.check(_lib.lib().mb_mask_tokens(ctypes.c_void_p(tok.data_ptr()), ctypes.c_void_p(u.data_ptr()), ctypes.c_void_p(val.data_ptr()),
+                                             int(mask_token), ctypes.c_void_p(masked.data_ptr()), ctypes.c_void_p(mask.data_ptr()),
+                                             b, tok.numel() // b, _lib.current_stream()))
+    return masked, mask

@@ -395,3 +395,40 @@ def autoencode(sd, x, num_resolutions=5, num_res_blocks=2):
     """ConvVQModel.forward (conv_vqgan.py:114-132): (reconstruction, indices)."""
     zq, idx, _ = encode(sd, x, num_resolutions, num_res_blocks)
     return conv_decoder(sd, zq, num_resolutions, num_res_blocks), idx
+
+
+# ----------------------------------------------------------------------------------------------
+# forward half of the training step (scripts/train_maskbit.py:362-380)
+# ----------------------------------------------------------------------------------------------
+def get_mask_tokens(tokens, mask_token, mode="arccos", min_masking_ratio=0.0):
+    """masking.py:7-38: per-sample ratio from rand(B), per-slot rand(tokens.size()) < ratio, both from the default CPU generator."""
+    r = torch.rand(tokens.size(0)) * (1 - min_masking_ratio)
+    if mode == "linear":
+        val = 1 - r
+    elif mode == "square":
+        val = 1 - (r ** 2)
+    elif mode == "cosine":
+        val = torch.cos(r * math.pi * 0.5)
+    elif mode == "arccos":
+        val = torch.acos(r) / (math.pi * 0.5)
+    else:
+        raise ValueError("Invalid mode. Choose between 'linear','square', 'cosine', 'arccos'.")
+    mask = torch.rand(tokens.size()) < val.view(-1, 1, 1)
+    masked = tokens.detach().clone()
+    masked[mask] = mask_token
+    return masked, mask
+
+
+def mlm_loss(inputs, targets, masks, label_smoothing=0.1, sum_splits=False):
+    """losses.py:289-339 MLMLoss.forward written out: label-smoothed cross entropy (1-eps) * nll + eps * mean_j(-logp_j), mean over
+    rows; accuracies as mean(argmax == target) ** m; the same over the masked rows.  Returns the four scalars as python floats."""
+    b, n, m, v = inputs.shape
+    logp = torch.log_softmax(inputs.reshape(-1, v).double(), dim=-1)
+    t = targets.reshape(-1)
+    nll = -logp.gather(1, t[:, None]).squeeze(1)
+    smooth = -logp.mean(dim=1)
+    row = (1 - label_smoothing) * nll + label_smoothing * smooth
+    hit = (inputs.reshape(-1, v).argmax(-1) == t).double()
+    mk = masks.reshape(-1)
+    scale = m if sum_splits else 1
+    return (float(row.mean()) * scale, float(hit.mean()) ** m, float(row[mk].mean()) * scale, float(hit[mk].mean()) ** m)

@@ -28,14 +28,20 @@ import select_cases as SC  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 # bf16 GEMM operands / bf16 residual stream with fp32 accumulation, LayerNorm and softmax, vs the fp32 reference:
-# the reference's own bf16-autocast run differs from its fp32 run by 3.0e-2 max / 5.4e-3 mean.
-LOGIT_MAX_ABS = 6e-2
-LOGIT_MEAN_ABS = 1e-2
+# the reference's own bf16-autocast run differs from its fp32 run by 3.2e-2 max / 5.5e-3 mean on the same checkpoint.
+# Measured on B200 over every forward test (profiles/r02_pytest_gpu.log): max 3.64e-2 (18-bit), mean 6.14e-3; the bars sit one
+# notch above that, so a regression of the bf16 pipeline fails instead of hiding inside a 2x margin.
+LOGIT_MAX_ABS = 4.5e-2
+LOGIT_MEAN_ABS = 7.5e-3
 PIXEL_MAX_ABS = 1e-3   # BASELINE.json north_star: decoded pixels within 1e-3 abs fp32
-STEP0_AGREEMENT_MIN = 0.95        # free-running step 0 vs the reference's tokens (argmax(p/q) flips under bf16 logits)
-TEACHER_FORCED_AGREEMENT_MIN = 0.90
-TRAINED_LIKE_MAX_REL = 2e-2       # trained-like checkpoint: max / mean logit error relative to the logit range
-TRAINED_LIKE_MEAN_REL = 3e-3
+# token agreement when the CUDA (bf16) logits replace the reference's fp32 logits in argmax(p / q): measured 0.9932 .. 0.9971
+# teacher-forced (4 steps), 0.9956 (12-bit) / 0.9941 (14-bit) at the free-running step 0 (profiles/r02_pytest_gpu.log)
+STEP0_AGREEMENT_MIN = 0.985
+TEACHER_FORCED_AGREEMENT_MIN = 0.985
+# trained-like checkpoint (logit range 13.8): measured max 8.8e-2 = 6.4e-3 of the range, mean 1.13e-2 = 8.2e-4 of the range
+# (the REFERENCE's own bf16-autocast run on this checkpoint: 8.2e-2 max / 1.48e-2 mean against its fp32 run)
+TRAINED_LIKE_MAX_REL = 1.0e-2
+TRAINED_LIKE_MEAN_REL = 1.1e-3
 
 
 def _p(t):
@@ -411,9 +417,9 @@ def test_sample_14bit_against_reference_run(golden_dir):
 
 def test_forward_trained_like_checkpoint(golden_dir):
     """A checkpoint with trained-like statistics (weights.trained_like_lfq_bert_state_dict: LayerNorm gains 0.1 .. 5 with outlier
-    channels, biases with a common offset and +-3 entries, wider projections -> logit range of tens): the bf16 pre-norm stream and
-    the folded LayerNorms against the reference's own fp32 logits (ADVICE r1 / VERDICT r1 weak #4).  The bar scales with the logit
-    range: the synthetic N(0, 0.02) checkpoints give |logit| < 1 and 3e-2 max error; here |logit| reaches 14."""
+    channels, biases with a common offset and +-3 entries, wider projections -> attention logits with a std of 3-4, output logit
+    range of 14): the bf16 pre-norm stream and the folded LayerNorms against the reference's own fp32 logits (ADVICE r1 / VERDICT r1
+    weak #4).  The bar scales with the logit range; the reference's own bf16-autocast run is the yardstick next to it."""
     from maskbit_b200.weights import trained_like_lfq_bert_state_dict
     g = np.load(os.path.join(golden_dir, "forward_trained_like_12bit.npz"))
     cfg = load_config("maskbit_generator_12bit")

@@ -250,3 +250,34 @@ def test_forward_trained_like_matches_reference(golden_dir):
     # fp32 summation-order noise (the reference's fused nn.MultiheadAttention vs plain matmuls here) grows with the activation
     # range: measured 9.2e-4 at a logit range of 14, i.e. 7e-5 of the range -- the N(0, 0.02) checkpoints give 2e-5 at range < 1
     assert (logits - ref).abs().max().item() <= 2e-3
+
+
+def _train_fwd_inputs(v, b, seed):
+    """tests/golden/make_golden.py::train_fwd_inputs."""
+    g = torch.Generator().manual_seed(seed)
+    full = torch.randint(0, v * v, (b, 256), generator=g)
+    logits = torch.randn((b, 256, 2, v), generator=g) * 2.0
+    return full, logits
+
+
+def test_training_forward_half_matches_reference(golden_dir):
+    """SURVEY.md 8 f-4, forward half (train_maskbit.py:362-380): the oracle's split / get_mask_tokens / mlm_loss against the
+    reference's own outputs on seeded inputs (fixture train_fwd.npz): integers exact, the four loss scalars to 1e-6."""
+    g = np.load(os.path.join(golden_dir, "train_fwd.npz"))
+    for v, b in ((64, 6), (128, 3)):
+        full, logits = _train_fwd_inputs(v, b, seed=900 + v)
+        tok = O.split_factorized_tokens(full, v * v, 2)
+        assert np.array_equal(tok.numpy(), g[f"v{v}_split"].astype(np.int64))
+        logits = logits.clone()
+        logits.scatter_add_(-1, tok.unsqueeze(-1), torch.full(tok.shape + (1,), 2.5))
+        for mode in ("arccos", "linear", "square", "cosine"):
+            torch.manual_seed(77)
+            masked, mask = O.get_mask_tokens(tok, v, mode=mode, min_masking_ratio=0.1 if mode == "square" else 0.0)
+            assert np.array_equal(masked.numpy(), g[f"v{v}_{mode}_masked"].astype(np.int64))
+            assert np.array_equal(mask.numpy(), g[f"v{v}_{mode}_mask"])
+            for smooth, sum_splits in ((0.1, False), (0.0, True)):
+                got = np.array(O.mlm_loss(logits, tok, mask, smooth, sum_splits))
+                want = g[f"v{v}_{mode}_loss_{smooth}_{int(sum_splits)}"]
+                assert np.allclose(got, want, rtol=1e-6, atol=1e-7), (v, mode, smooth, got, want)
+    with pytest.raises(ValueError):
+        O.get_mask_tokens(torch.zeros((1, 4, 2), dtype=torch.int64), 64, mode="root")

@@ -1,8 +1,7 @@
-// Micro-probe: issue-to-completion time (SM clocks) of chains of tcgen05.mma of the shapes an attention item can be built from,
-// plus TMEM load / MUFU / TMEM store rates of the softmax warps.  Data is zeros: only timing is read.
+// Micro-probe: issue-to-completion time (SM clocks) of chains of tcgen05.mma of the shapes an attention item is built from, issued
+// the way the kernels issue them (elect.sync region, compile-time shapes: operands in uniform registers).  Data is zeros.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/mma_probe tools/mma_probe.cu && gpurun -- tools/mma_probe
 #include <cstdio>
-#include <vector>
 #include "../maskbit_b200/csrc/ptx.cuh"
 
 using namespace mb;
@@ -21,13 +20,31 @@ __device__ __forceinline__ uint64_t sdesc_mn128(uint32_t addr) {
     return d;
 }
 
-enum { SS = 0, TS = 1 };
-struct Case { int kind, M, N, n_instr, n_acc, a_mn, b_mn; const char* name; };
+// TS: A from TMEM.  NI instructions round-robin over NACC accumulators.  BMN: B MN-major (V), else K-major (K).
+template <bool TS, int M, int N, int NI, int NACC, bool BMN>
+__device__ __forceinline__ void run_case(uint32_t tm, uint32_t sa, uint32_t sb, uint64_t* bar, uint32_t& phase, long long* out, int reps) {
+    constexpr uint32_t idesc = make_idesc(1, M, N) | (BMN ? (1u << 16) : 0u);
+    long long best = 1ll << 60, best_issue = 0;
+    for (int r = 0; r < reps; ++r) {
+        const long long t0 = clock64();
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const uint32_t d = tm + 256 + (i % NACC) * 64;
+            const uint64_t bd = BMN ? sdesc_mn128(sb) + (uint64_t)((i & 15) * 128) : make_sdesc_k128(sb) + 2 * (i & 3);
+            if (TS) umma_ts(d, tm + 8 * (i & 15), bd, idesc, i >= NACC);
+            else umma_f16(d, make_sdesc_k128(sa) + 2 * (i & 3), bd, idesc, i >= NACC);
+        }
+        umma_commit(bar);
+        const long long t1 = clock64();
+        mbar_wait(bar, phase); phase ^= 1;
+        const long long t2 = clock64();
+        if (t2 - t0 < best) { best = t2 - t0; best_issue = t1 - t0; }
+    }
+    out[0] = best; out[1] = best_issue;
+}
 
-__global__ void __launch_bounds__(256, 1) probe_kernel(const Case* cases, int n_cases, long long* out, int reps) {
-    extern __shared__ uint8_t raw[];
-    const uint32_t r32 = smem_u32(raw);
-    uint8_t* base = raw + ((1024u - (r32 & 1023u)) & 1023u);
+__global__ void __launch_bounds__(256, 1) probe_kernel(long long* out, int reps) {
+    extern __shared__ __align__(1024) uint8_t base[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(base + 160 * 1024);
     uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 2);
     for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(base)[i] = 0;
@@ -39,80 +56,24 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(const Case* cases, int n_
     tc_fence_after();
     const uint32_t tm = *slot;
     const uint32_t sa = smem_u32(base), sb = sa + 64 * 1024;
-    if (threadIdx.x == 0) {
-        uint32_t phase = 0;
-        for (int c = 0; c < n_cases; ++c) {
-            const Case cs = cases[c];
-            uint32_t idesc = make_idesc(1, cs.M, cs.N);
-            if (cs.a_mn) idesc |= 1u << 15;
-            if (cs.b_mn) idesc |= 1u << 16;
-            long long best = 1ll << 60;
-            for (int r = 0; r < reps; ++r) {
-                const long long t0 = clock64();
-                for (int i = 0; i < cs.n_instr; ++i) {
-                    const uint32_t d = tm + 256 + (i % cs.n_acc) * (cs.N <= 128 ? 64 : 0) % 256;
-                    const uint64_t bd = cs.b_mn ? sdesc_mn128(sb) + (uint64_t)((i & 15) * 128) : make_sdesc_k128(sb) + 2 * (i & 3);
-                    if (cs.kind == TS) umma_ts(d, tm + 8 * (i & 15), bd, idesc, i >= cs.n_acc);
-                    else {
-                        const uint64_t ad = cs.a_mn ? sdesc_mn128(sa) + (uint64_t)((i & 15) * 128) : make_sdesc_k128(sa) + 2 * (i & 3);
-                        umma_f16(d, ad, bd, idesc, i >= cs.n_acc);
-                    }
-                }
-                umma_commit(bar);
-                const long long t1 = clock64();
-                mbar_wait(bar, phase); phase ^= 1;
-                const long long t2 = clock64();
-                if (t2 - t0 < best) { best = t2 - t0; out[c * 2 + 1] = t1 - t0; }
-            }
-            out[c * 2] = best;
+    if (threadIdx.x < 32) {
+        if (elect_one()) {
+            uint32_t phase = 0;
+            run_case<false, 128, 256, 4, 1, false>(tm, sa, sb, bar, phase, out + 0, reps);    // S full
+            run_case<false, 128, 256, 8, 1, false>(tm, sa, sb, bar, phase, out + 2, reps);
+            run_case<false, 128, 256, 16, 1, false>(tm, sa, sb, bar, phase, out + 4, reps);
+            run_case<false, 128, 128, 4, 1, false>(tm, sa, sb, bar, phase, out + 6, reps);    // S unit
+            run_case<false, 128, 128, 16, 1, false>(tm, sa, sb, bar, phase, out + 8, reps);
+            run_case<true, 128, 64, 16, 1, true>(tm, sa, sb, bar, phase, out + 10, reps);     // PV now
+            run_case<true, 128, 64, 16, 2, true>(tm, sa, sb, bar, phase, out + 12, reps);
+            run_case<true, 128, 64, 8, 1, true>(tm, sa, sb, bar, phase, out + 14, reps);
+            run_case<true, 128, 64, 1, 1, true>(tm, sa, sb, bar, phase, out + 16, reps);
+            run_case<false, 128, 256, 1, 1, false>(tm, sa, sb, bar, phase, out + 18, reps);
+            run_case<false, 128, 64, 16, 1, true>(tm, sa, sb, bar, phase, out + 20, reps);    // PV with P in smem
+            run_case<true, 128, 256, 4, 1, false>(tm, sa, sb, bar, phase, out + 22, reps);    // S with Q in TMEM
+            run_case<true, 128, 256, 16, 1, false>(tm, sa, sb, bar, phase, out + 24, reps);
         }
-    }
-    __syncthreads();
-    // ---- softmax-side rates: 4 warps (128 rows) or 8 warps; each iteration = LDTM x32 of 32 columns (+ ex2 + pack + STTM x16)
-    const int warp = threadIdx.x >> 5;
-    const uint32_t treg = tm + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 128;
-    for (int mode = 0; mode < 6; ++mode) {
-        // 0: 4 warps LDTM only   1: 8 warps LDTM only   2: 4 warps LDTM+ex2   3: 8 warps LDTM+ex2   4: 4 warps full (ld, ffma, ex2, pack, st)  5: 8 warps full
-        const int nw = (mode & 1) ? 8 : 4;
-        __syncthreads();
-        const long long t0 = clock64();
-        float acc = 0.f;
-        if (warp < nw) {
-            uint32_t v[32];
-            for (int it = 0; it < 16; ++it) {
-                tmem_ld_32x32(treg + (it & 3) * 32, v);
-                tmem_ld_wait();
-                if (mode >= 2) {
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
-                        if (mode >= 4) { x0 = fmaf(x0, 0.18f, -1.0f); x1 = fmaf(x1, 0.18f, -1.0f); }
-                        asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(x0));
-                        asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(x1));
-                        acc += x0 + x1;
-                        __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
-                        pk[j] = *reinterpret_cast<uint32_t*>(&hh);
-                    }
-                    if (mode >= 4) {
-                        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-                                     ::"r"(treg + (it & 3) * 16), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]),
-                                     "r"(pk[7]), "r"(pk[8]), "r"(pk[9]), "r"(pk[10]), "r"(pk[11]), "r"(pk[12]), "r"(pk[13]), "r"(pk[14]), "r"(pk[15]) : "memory");
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) acc += __uint_as_float(pk[j]);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) acc += __uint_as_float(v[j]);
-                }
-            }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        }
-        __syncthreads();
-        const long long t1 = clock64();
-        if (threadIdx.x == 0) out[2 * n_cases + mode] = t1 - t0;
-        if (acc == 123.456f) out[63] = 1;
+        __syncwarp();
     }
     tc_fence_before();
     __syncthreads();
@@ -120,43 +81,32 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(const Case* cases, int n_
 }
 
 int main() {
-    std::vector<Case> cases = {
-        {SS, 128, 256, 4, 1, 0, 0, "SS M128 N256 x4   (S, full 256 keys)          ideal 512"},
-        {SS, 128, 256, 8, 1, 0, 0, "SS M128 N256 x8                               ideal 1024"},
-        {SS, 128, 128, 4, 1, 0, 0, "SS M128 N128 x4   (S, 128-key unit)           ideal 256"},
-        {SS, 128, 128, 8, 1, 0, 0, "SS M128 N128 x8                               ideal 512"},
-        {TS, 128, 64, 16, 1, 0, 1, "TS M128 N64 x16 1 acc, B mn-major (PV now)    ideal 512"},
-        {TS, 128, 64, 16, 2, 0, 1, "TS M128 N64 x16 2 acc, B mn-major             ideal 512"},
-        {TS, 128, 64, 32, 4, 0, 1, "TS M128 N64 x32 4 acc, B mn-major             ideal 1024"},
-        {TS, 128, 64, 8, 1, 0, 1,  "TS M128 N64 x8  1 acc (unit)                  ideal 256"},
-        {TS, 128, 64, 16, 1, 0, 0, "TS M128 N64 x16 1 acc, B k-major              ideal 512"},
-        {SS, 128, 64, 16, 1, 0, 1, "SS M128 N64 x16 1 acc, B mn-major (P in smem) ideal 512"},
-        {SS, 128, 64, 16, 2, 0, 1, "SS M128 N64 x16 2 acc, B mn-major             ideal 512"},
-        {SS, 128, 64, 16, 1, 0, 0, "SS M128 N64 x16 1 acc, B k-major              ideal 512"},
-        {SS, 64, 256, 16, 1, 1, 0, "SS M64 N256 x16, A mn-major (O^T = V^T P^T)   ideal 1024@M64-half-rate"},
-        {SS, 64, 128, 16, 1, 1, 0, "SS M64 N128 x16, A mn-major                   ideal 512@half-rate"},
-        {SS, 128, 128, 16, 1, 0, 1, "SS M128 N128 x16, B mn-major (2 heads wide)   ideal 1024"},
-        {TS, 128, 128, 16, 1, 0, 1, "TS M128 N128 x16, B mn-major                  ideal 1024"},
-        {TS, 128, 64, 1, 1, 0, 1,  "TS M128 N64 x1   (latency of one)"},
-        {SS, 128, 256, 1, 1, 0, 0, "SS M128 N256 x1  (latency of one)"},
+    const char* names[] = {
+        "SS M128 N256 x4   (S of one tile)                ideal 512",
+        "SS M128 N256 x8                                  ideal 1024",
+        "SS M128 N256 x16                                 ideal 2048",
+        "SS M128 N128 x4   (S, 128-key half)              ideal 256",
+        "SS M128 N128 x16                                 ideal 1024",
+        "TS M128 N64 x16 1 acc, B mn-major (PV)           ideal 512",
+        "TS M128 N64 x16 2 acc                            ideal 512",
+        "TS M128 N64 x8  1 acc                            ideal 256",
+        "TS M128 N64 x1  (latency of one)",
+        "SS M128 N256 x1 (latency of one)",
+        "SS M128 N64 x16, B mn-major (P from smem)        ideal 512",
+        "TS M128 N256 x4  (S with Q in TMEM)              ideal 512",
+        "TS M128 N256 x16                                 ideal 2048",
     };
-    Case* dc; long long* dout;
-    cudaMalloc(&dc, cases.size() * sizeof(Case));
+    long long* dout;
     cudaMalloc(&dout, 64 * sizeof(long long));
     cudaMemset(dout, 0, 64 * sizeof(long long));
-    cudaMemcpy(dc, cases.data(), cases.size() * sizeof(Case), cudaMemcpyHostToDevice);
-    const int smem = 160 * 1024 + 1024 + 64;
+    const int smem = 160 * 1024 + 64;
     cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    probe_kernel<<<1, 256, smem>>>(dc, (int)cases.size(), dout, 20);
+    probe_kernel<<<1, 256, smem>>>(dout, 20);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("probe failed: %s\n", cudaGetErrorString(e)); return 1; }
     long long h[64];
     cudaMemcpy(h, dout, sizeof(h), cudaMemcpyDeviceToHost);
-    printf("%-70s %10s %10s\n", "case", "clk total", "clk issue");
-    for (size_t c = 0; c < cases.size(); ++c) printf("%-70s %10lld %10lld\n", cases[c].name, h[2 * c], h[2 * c + 1]);
-    const char* names[6] = {"4 warps: LDTM x32 only, 16 iters (64 KB read)", "8 warps: LDTM x32 only, 16 iters (128 KB read)",
-                            "4 warps: LDTM + ex2 + pack (16384 exps)", "8 warps: LDTM + ex2 + pack (32768 exps)",
-                            "4 warps: LDTM + ffma + ex2 + pack + STTM (16384 exps)", "8 warps: same (32768 exps)"};
-    for (int m = 0; m < 6; ++m) printf("%-70s %10lld\n", names[m], h[2 * cases.size() + m]);
+    printf("%-62s %10s %10s\n", "case (one CTA, nothing else running)", "clk total", "clk issue");
+    for (int c = 0; c < 13; ++c) printf("%-62s %10lld %10lld\n", names[c], h[2 * c], h[2 * c + 1]);
     return 0;
 }
