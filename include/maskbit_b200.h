@@ -78,8 +78,13 @@ int mb_finalize(mb_handle* h, int model);
  *   labels  device int64 [n_label_rows]; sequence i reads labels[i % n_label_rows]
  *   drop    device uint8 [n_seq] (1 = replace label by the drop class) or NULL = drop all (drop_label_mask=None)
  *   logits  device fp32 [n_seq, seq_len, splits, V]  (class-token row already removed, bert.py:503) */
+/* mb_generator_forward_attn: the same with return_attn=True (bert.py:505-506): additionally writes
+ *   attn    device fp32 [depth, n_seq, seq_len + 1, seq_len + 1], layer l = the head-averaged attention weights
+ *           nn.MultiheadAttention(need_weights=True) returns in that layer (bert.py:119,137) */
 int mb_generator_forward(mb_handle* h, const int64_t* tokens, int n_token_rows, const int64_t* labels, int n_label_rows,
                          const uint8_t* drop, int n_seq, float* logits, mb_stream stream);
+int mb_generator_forward_attn(mb_handle* h, const int64_t* tokens, int n_token_rows, const int64_t* labels, int n_label_rows,
+                         const uint8_t* drop, int n_seq, float* logits, float* attn, mb_stream stream);
 
 /* One step of the select path (sampling.py:90-131) for B samples.
  *   logits_c / logits_u   device fp32 [B, seq_stride, splits, V]; logits_u NULL = no guidance (sampling.py:100-101)

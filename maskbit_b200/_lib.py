@@ -51,6 +51,7 @@ SYMBOLS = {
     "mb_set_tensor": (_I, [_P, _I, ctypes.c_char_p, _P, ctypes.POINTER(ctypes.c_int64), _I, _I]),
     "mb_finalize": (_I, [_P, _I]),
     "mb_generator_forward": (_I, [_P, _P, _I, _P, _I, _P, _I, _P, _P]),
+    "mb_generator_forward_attn": (_I, [_P, _P, _I, _P, _I, _P, _I, _P, _P, _P]),
     "mb_select_step": (_I, [_P, ctypes.POINTER(MBSelectArgs), _P]),
     "mb_decode_tokens": (_I, [_P, _P, _I, _P, _P]),
     "mb_encode": (_I, [_P, _P, _I, _P, _P, _P]),
@@ -92,8 +93,8 @@ def lib():
                 f"or `bash maskbit_b200/csrc/build.sh`. maskbit_b200 has no CPU or PyTorch fallback.")
         L = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SYMBOLS.items():
-            if name.startswith("mb_test_") and os.environ.get("MASKBIT_B200_LIB") and not hasattr(L, name):
-                continue   # A/B builds of older sources (tools/build_variants.sh) may predate a test hook
+            if os.environ.get("MASKBIT_B200_LIB") and not hasattr(L, name):
+                continue   # A/B builds of older sources (tools/build_variants.sh) may predate an entry point
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args

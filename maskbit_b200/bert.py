@@ -61,10 +61,10 @@ class LFQBert(EngineModel):
     @torch.no_grad()
     def forward(self, img_tokens, class_labels, drop_label_mask=None, return_attn=False):
         """bert.py:456-508.  img_tokens int64 [N, seq_len, splits], class_labels int64 [N], drop_label_mask bool [N]
-        or None (= drop every label, the reference's behaviour for None).  Returns fp32 [N, seq_len, splits, V].
+        or None (= drop every label, the reference's behaviour for None).  Returns fp32 [N, seq_len, splits, V]; with
+        return_attn=True (bert.py:505-506) the pair (logits, [depth tensors fp32 [N, seq_len+1, seq_len+1]]): per layer the
+        head-averaged attention weights of nn.MultiheadAttention(need_weights=True), computed by a side kernel per layer.
         Unlike the reference (bert.py:484) the caller's class_labels tensor is not modified."""
-        if return_attn:
-            raise NotImplementedError("return_attn=True (per-layer attention maps) is not provided by the fused attention kernel")
         h = self._engine()
         dev = self._device
         tok = img_tokens.to(device=dev, dtype=torch.int64).contiguous()
@@ -80,6 +80,13 @@ class LFQBert(EngineModel):
             drop_ptr = ctypes.c_void_p(drop.data_ptr())
         with torch.cuda.device(dev):
             logits = torch.empty((n, self.seq_len, self.splits, self.effective_codebook_size), dtype=torch.float32, device=dev)
+            if return_attn:
+                s = self.seq_len + 1
+                attn = torch.empty((self.depth, n, s, s), dtype=torch.float32, device=dev)
+                _lib.check(_lib.lib().mb_generator_forward_attn(h, ctypes.c_void_p(tok.data_ptr()), n, ctypes.c_void_p(lab.data_ptr()), n,
+                                                                drop_ptr, n, ctypes.c_void_p(logits.data_ptr()),
+                                                                ctypes.c_void_p(attn.data_ptr()), _lib.current_stream()))
+                return logits, list(attn.unbind(0))
             _lib.check(_lib.lib().mb_generator_forward(h, ctypes.c_void_p(tok.data_ptr()), n, ctypes.c_void_p(lab.data_ptr()), n,
                                                        drop_ptr, n, ctypes.c_void_p(logits.data_ptr()), _lib.current_stream()))
         return logits

@@ -874,7 +874,7 @@ static int run_attention(mb_handle* h, const CUtensorMap& tm_big, const CUtensor
 }
 
 static int forward_impl(mb_handle* h, const int64_t* tokens, int n_token_rows, const int64_t* labels, int n_label_rows,
-                        const uint8_t* drop, int n_seq, float* logits, cudaStream_t st) {
+                        const uint8_t* drop, int n_seq, float* logits, cudaStream_t st, float* attn = nullptr) {
     if (!h->finalized[MB_GENERATOR]) return fail(MB_ERR_STATE, "generator weights not loaded (mb_set_tensor + mb_finalize)");
     if (n_seq <= 0 || n_token_rows <= 0 || n_label_rows <= 0) return fail(MB_ERR_INVALID, "forward: empty batch");
     MB_TRY(ensure_ws(h, n_seq));
@@ -899,6 +899,12 @@ static int forward_impl(mb_handle* h, const int64_t* tokens, int n_token_rows, c
         // attention block (bert.py:137-139): yB = out_proj(MHA(LN(yA))) + LN(yA)
         MB_TRY(run_linear(h, MB_PROF_GEMM_QKV, h->tm_yA, L.qkv, M, EPI_LNIN_BF16, nullptr, h->stA, nullptr, h->qkv, &h->tmo_qkv, 3 * D, st));
         MB_TRY(run_attention(h, h->tm_qkv_big, h->tm_qkv_row, h->tmo_att, h->qkv, h->att, n_seq, h->S, D, c.heads, h->num_sms, st));
+        if (attn) {   // return_attn=True: this layer's head-averaged attention map, from the same qkv buffer (diagnostic side path)
+            ProfScope prof(h, MB_PROF_ATTENTION, st);
+            attention_probs_kernel<<<dim3(n_seq, (h->S + 31) / 32), 256, 0, st>>>(h->qkv, attn + (size_t)l * n_seq * h->S * h->S, h->S, D, c.heads,
+                                                                                  1.4426950408889634f / sqrtf((float)ATT_HD));
+            CU_TRY(cudaGetLastError()); h->launches++;
+        }
         MB_TRY(run_linear(h, MB_PROF_GEMM_OUT, h->tm_att, L.out, M, EPI_RES_LN_BF16_STATS, h->yA, res_stA, h->stB, h->yB, &h->tmo_yB, D, st, 0, 0, &h->tmo_yA));
         // feed-forward block (bert.py:69-70): yA = W2 gelu(W1 LN1(yB) + b1) + b2 + LN1(yB)
         MB_TRY(run_linear(h, MB_PROF_GEMM_UP, h->tm_yB, L.up, M, EPI_LNIN_GELU_BF16, nullptr, h->stB, nullptr, h->hmid, &h->tmo_hmid, c.mlp_dim, st));
@@ -920,6 +926,12 @@ extern "C" int mb_generator_forward(mb_handle* h, const int64_t* tokens, int n_t
                                     int n_label_rows, const uint8_t* drop, int n_seq, float* logits, mb_stream stream) {
     if (!h || !tokens || !labels || !logits) return fail(MB_ERR_INVALID, "mb_generator_forward: null argument");
     return forward_impl(h, tokens, n_token_rows, labels, n_label_rows, drop, n_seq, logits, (cudaStream_t)stream);
+}
+extern "C" int mb_generator_forward_attn(mb_handle* h, const int64_t* tokens, int n_token_rows, const int64_t* labels, int n_label_rows,
+                                         const uint8_t* drop, int n_seq, float* logits, float* attn, mb_stream stream) {
+    if (!h || !tokens || !labels || !logits || !attn) return fail(MB_ERR_INVALID, "mb_generator_forward_attn: null argument");
+    if (h->S > ATTP_KEYS) return fail(MB_ERR_INVALID, "attention maps: sequence length %d > %d", h->S, ATTP_KEYS);
+    return forward_impl(h, tokens, n_token_rows, labels, n_label_rows, drop, n_seq, logits, (cudaStream_t)stream, attn);
 }
 
 // ------------------------------------------------------------------------------------------------ select

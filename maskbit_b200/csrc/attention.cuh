@@ -207,3 +207,77 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 }
 
 }  // namespace mb
+
+// ------------------------------------------------------------------------------------------------ attention maps (return_attn=True)
+// probs fp32 [n_seq][S][S]: softmax(Q K^T / sqrt(64)) averaged over the heads -- what nn.MultiheadAttention(need_weights=True,
+// average_attn_weights=True) hands back (reference bert.py:119,137 with return_attn=True; bert.py:505-506 returns one per layer).
+// A diagnostic side path on CUDA cores, run per layer on the qkv buffer the fused attention kernel consumes; the fused kernel itself
+// never materialises the maps.  grid = (n_seq, ceil(S / 32)), 8 warps x 4 query rows; one head's K tile in shared memory at a time
+// (rows padded to 33 words: lane j reads row j at the same word, conflict-free).
+namespace mb {
+constexpr int ATTP_KEYS = 288;                      // 9 x 32 key slots >= ATT_MAXS
+constexpr int ATTP_SMEM_BYTES = ATTP_KEYS * 33 * 4;
+
+__global__ void __launch_bounds__(256)
+attention_probs_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ probs, int S, int D, int H, float sl2) {
+    __shared__ uint32_t ks[ATTP_KEYS * 33];
+    const int seq = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = blockIdx.y * 32 + warp * 4;
+    const float inv_h = 1.0f / (float)H;
+    float acc[4][9];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[rr][t] = 0.f;
+    for (int h = 0; h < H; ++h) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < ATTP_KEYS * 32; idx += 256) {
+            const int r = idx >> 5, w = idx & 31;
+            ks[r * 33 + w] = r < S ? reinterpret_cast<const uint32_t*>(qkv + ((size_t)seq * S + r) * 3 * D + D + h * 64)[w] : 0u;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            const int i = row0 + rr;
+            if (i >= S) continue;                                   // warp-uniform
+            const uint32_t qreg = reinterpret_cast<const uint32_t*>(qkv + ((size_t)seq * S + i) * 3 * D + h * 64)[lane];
+            float sc[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) sc[t] = 0.f;
+            for (int d2 = 0; d2 < 32; ++d2) {
+                const uint32_t qw = __shfl_sync(0xffffffffu, qreg, d2);
+                const float q0 = __uint_as_float(qw << 16), q1 = __uint_as_float(qw & 0xffff0000u);
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const uint32_t kw = ks[(lane + 32 * t) * 33 + d2];
+                    sc[t] = fmaf(q0, __uint_as_float(kw << 16), fmaf(q1, __uint_as_float(kw & 0xffff0000u), sc[t]));
+                }
+            }
+            float mx = -INFINITY;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) if (lane + 32 * t < S) mx = fmaxf(mx, sc[t]);
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            float sum = 0.f;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                sc[t] = lane + 32 * t < S ? exp2f((sc[t] - mx) * sl2) : 0.f;
+                sum += sc[t];
+            }
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float w = inv_h / sum;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) acc[rr][t] = fmaf(sc[t], w, acc[rr][t]);
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+        const int i = row0 + rr;
+        if (i >= S) continue;
+        float* dst = probs + ((size_t)seq * S + i) * S;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) if (lane + 32 * t < S) dst[lane + 32 * t] = acc[rr][t];
+    }
+}
+}  // namespace mb

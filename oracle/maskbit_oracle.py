@@ -79,8 +79,9 @@ def preprocess_tokens(img_tokens, bits, splits):
     return t.reshape(img_tokens.shape[0], img_tokens.shape[1], splits * eff)
 
 
-def mha(x, w_in, b_in, w_out, b_out, heads):
-    """nn.MultiheadAttention(batch_first, eval) (bert.py:84,137): packed in-proj, softmax(QK^T/sqrt(d))V, out-proj."""
+def mha(x, w_in, b_in, w_out, b_out, heads, attn_out=None):
+    """nn.MultiheadAttention(batch_first, eval) (bert.py:84,137): packed in-proj, softmax(QK^T/sqrt(d))V, out-proj.
+    attn_out, if a list, receives the head-averaged weights [N, S, S] (need_weights=True, average_attn_weights=True)."""
     n, s, d = x.shape
     hd = d // heads
     qkv = x @ w_in.t() + b_in
@@ -89,11 +90,13 @@ def mha(x, w_in, b_in, w_out, b_out, heads):
     k = k.view(n, s, heads, hd).transpose(1, 2)
     v = v.view(n, s, heads, hd).transpose(1, 2)
     att = torch.softmax((q @ k.transpose(-1, -2)) * (1.0 / math.sqrt(hd)), dim=-1)
+    if attn_out is not None:
+        attn_out.append(att.mean(dim=1))
     o = (att @ v).transpose(1, 2).reshape(n, s, d)
     return o @ w_out.t() + b_out
 
 
-def _trunk_and_head(sd, x, heads):
+def _trunk_and_head(sd, x, heads, attn_out=None):
     """first_layer -> TransformerEncoder (post- or pre-norm) -> [norm_after_transformer] -> last_layer, shared by LFQBert
     (bert.py:496-500) and Bert (bert.py:324-328).  Returns (head output, per-layer hidden states)."""
     prenorm = "norm_after_transformer.weight" in sd
@@ -105,7 +108,7 @@ def _trunk_and_head(sd, x, heads):
 
         def attn(t):
             return mha(t, sd[p + "0.mha.in_proj_weight"], sd[p + "0.mha.in_proj_bias"],
-                       sd[p + "0.mha.out_proj.weight"], sd[p + "0.mha.out_proj.bias"], heads)
+                       sd[p + "0.mha.out_proj.weight"], sd[p + "0.mha.out_proj.bias"], heads, attn_out)
 
         def mlp(t):
             h = gelu_erf(t @ sd[p + "1.net.0.weight"].t() + sd[p + "1.net.0.bias"])
@@ -126,7 +129,7 @@ def _trunk_and_head(sd, x, heads):
 
 
 def lfq_bert_forward(sd, img_tokens, class_labels, drop_label_mask, *, heads=16, splits=2, nclass=1000,
-                     return_hidden=False):
+                     return_hidden=False, return_attn=False):
     """LFQBert.forward (bert.py:456-508), post-norm, or pre-norm when the checkpoint carries ``norm_after_transformer``
     (use_prenorm=True: bert.py:49-59,106-123,407-408,498-499).  Returns fp32 logits [N, seq_len, splits, V].
 
@@ -144,10 +147,13 @@ def lfq_bert_forward(sd, img_tokens, class_labels, drop_label_mask, *, heads=16,
     cls_emb = sd["class_emb.weight"][cls][:, None, :]
     proj = x_bits @ sd["input_proj.weight"].t() + sd["input_proj.bias"]
     x = torch.cat([proj, cls_emb], dim=1) + sd["pos_emb"]
-    y, hidden = _trunk_and_head(sd, x, heads)
+    attn = [] if return_attn else None
+    y, hidden = _trunk_and_head(sd, x, heads, attn)
     logits = y @ sd["prediction_layer.weight"].t() + sd["prediction_layer.bias"]
     v = logits.shape[-1] // splits
     logits = logits.view(n, seq_len + 1, splits, v)[:, :seq_len]                            # bert.py:502-503
+    if return_attn:
+        return logits, attn                                                                 # bert.py:505-506
     if return_hidden:
         return logits, hidden
     return logits

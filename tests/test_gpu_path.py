@@ -142,6 +142,28 @@ def test_forward_prenorm_matches_reference_golden(golden_dir):
         post.load_state_dict(sd, strict=True)          # the post-norm model has no norm_after_transformer
 
 
+def test_forward_return_attn_matches_reference_golden(golden_dir):
+    """return_attn=True (bert.py:505-506): (logits, one head-averaged attention map per layer) against the reference's own output on
+    a 2-layer generator with wide weights (attention rows far from uniform); rows sum to 1; logits equal the plain forward's."""
+    from maskbit_b200.weights import synthetic_lfq_bert_state_dict
+    g = np.load(os.path.join(golden_dir, "forward_attn_12bit.npz"))
+    gen = LFQBert(img_size=256, hidden_dim=1024, codebook_size=4096, codebook_splits=2, depth=2, heads=16, mlp_dim=4096,
+                  dropout=0.1, use_prenorm=False, input_stride=16)
+    gen.load_state_dict(synthetic_lfq_bert_state_dict(seed=4, codebook_size=4096, depth=2, weight_std=0.05), strict=True)
+    gen = gen.to("cuda")
+    tok, lab, drop = (torch.from_numpy(g["tokens"].astype(np.int64)).cuda(), torch.from_numpy(g["labels"]).cuda(), torch.from_numpy(g["drop"]).cuda())
+    logits, attn = gen(tok, lab, drop, return_attn=True)
+    assert isinstance(attn, list) and len(attn) == 2 and attn[0].shape == (2, 257, 257) and attn[0].dtype == torch.float32
+    assert torch.equal(logits, gen(tok, lab, drop))
+    ref = torch.from_numpy(g["attn_seq0"]).cuda()
+    got = torch.stack([a[0] for a in attn])
+    d = (got - ref).abs()
+    print(f"return_attn: max abs diff of the attention maps {d.max().item():.3e} (largest weight {ref.max().item():.3f}); "
+          f"logits max abs {(logits.cpu() - torch.from_numpy(g['logits'])).abs().max().item():.3e}")
+    assert d.max().item() <= 2e-3 * max(1.0, ref.max().item() / 0.05)          # q, k are bf16 outputs of the QKV GEMM
+    assert (torch.stack(attn).sum(-1) - 1.0).abs().max().item() <= 1e-5
+
+
 def test_forward_bert_matches_reference_golden(golden_dir):
     """Bert, the embedding-table generator (bert.py:184-340; model_cls "bert"): token-embedding gather, the shared trunk, the tied
     output projection and the per-position bias, against the reference's own logits; then a short guided sample() through it."""
@@ -180,9 +202,6 @@ def test_forward_rejects_bad_input():
     _, _, _, gen = models(12)
     with pytest.raises(ValueError):
         gen(torch.zeros((2, 255, 2), dtype=torch.int64, device="cuda"), torch.zeros(2, dtype=torch.int64, device="cuda"))
-    with pytest.raises(NotImplementedError):
-        gen(torch.zeros((1, 256, 2), dtype=torch.int64, device="cuda"), torch.zeros(1, dtype=torch.int64, device="cuda"),
-            None, return_attn=True)
 
 
 # ------------------------------------------------------------------------------------------------ P1 select

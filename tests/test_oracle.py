@@ -66,6 +66,17 @@ def test_forward_prenorm_matches_reference(golden_dir):
     assert (logits - torch.from_numpy(g["logits"])).abs().max().item() <= 2e-5
 
 
+def test_forward_return_attn_matches_reference(golden_dir):
+    """return_attn=True (bert.py:505-506): logits and the per-layer head-averaged attention weights of the reference."""
+    from maskbit_b200.weights import synthetic_lfq_bert_state_dict
+    g = np.load(os.path.join(golden_dir, "forward_attn_12bit.npz"))
+    sd = synthetic_lfq_bert_state_dict(seed=4, codebook_size=4096, depth=2, weight_std=0.05)
+    logits, attn = O.lfq_bert_forward(sd, torch.from_numpy(g["tokens"].astype(np.int64)), torch.from_numpy(g["labels"]),
+                                      torch.from_numpy(g["drop"]), return_attn=True)
+    assert (logits - torch.from_numpy(g["logits"])).abs().max().item() <= 5e-5
+    assert len(attn) == 2 and (torch.stack([a[0] for a in attn]) - torch.from_numpy(g["attn_seq0"])).abs().max().item() <= 1e-6
+
+
 def test_forward_bert_matches_reference(golden_dir):
     """The embedding-table generator (bert.py:184-340) restated in the oracle against the reference's own logits."""
     from maskbit_b200.weights import synthetic_bert_state_dict
