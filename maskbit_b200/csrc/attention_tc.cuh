@@ -201,7 +201,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
                 const int st = it & 1;
                 const uint32_t sq = smem0 + st * ATC_STAGE_BYTES, sk = sq + ATC_TILE_BYTES, sv = sk + ATC_TILE_BYTES;
                 mbar_wait(&fullqk[st], (it >> 1) & 1);
+                ATC_EV(5 + t, 0, it);
                 mbar_wait(&t_free[t], (it & 1) ^ 1);
+                ATC_EV(5 + t, 1, it);
                 tc_fence_after();
                 {                                                               // S_t = Q_t K^T
                     const uint64_t a = make_sdesc_k128(sq + t * 128 * 128), b = make_sdesc_k128(sk);
@@ -212,7 +214,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
                     ATC_EV(1, t, it);
                 }
                 mbar_wait(&p_full[t], it & 1);
+                ATC_EV(5 + t, 2, it);
                 mbar_wait(&fullv[st], (it >> 1) & 1);
+                ATC_EV(5 + t, 3, it);
                 tc_fence_after();
                 {                                                               // O_t = P_t V
                     const uint64_t b = make_sdesc_mn128(sv);
