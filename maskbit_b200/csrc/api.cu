@@ -50,6 +50,26 @@ static int fail(int code, const char* fmt, ...) {
 extern "C" const char* mb_last_error(void) { return g_err.c_str(); }
 extern "C" const char* mb_version(void) { return "maskbit_b200 0.1 sm_100a"; }
 
+// ------------------------------------------------------------------------------------------------ launches
+// Kernels of the generator trunk are launched with programmatic stream serialization (ptx.cuh: pdl_wait): each one's prologue and
+// launch latency overlap its predecessor's tail -- at small batches a forward is ~120 launches of a few microseconds each.
+// MASKBIT_B200_PDL=0 falls back to plain stream order (A/B timing).
+static bool use_pdl() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MASKBIT_B200_PDL"); v = e ? (atoi(e) != 0) : 1; }
+    return v != 0;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = use_pdl() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 // ------------------------------------------------------------------------------------------------ TMA descriptors
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -746,16 +766,16 @@ static int launch_gemm_bn(mb_handle* h, const CUtensorMap& ta, const CUtensorMap
     const int grid = tiles < num_sms ? tiles : num_sms;
     const int smem = GemmCfg<BN>::SMEM_BYTES;
     switch (epi) {
-        case 0: gemm_bf16_tcgen05_kernel<BN, 0><<<grid, 384, smem, st>>>(ta, tb, p); break;
-        case 1: gemm_bf16_tcgen05_kernel<BN, 1><<<grid, 384, smem, st>>>(ta, tb, p); break;
-        case 2: gemm_bf16_tcgen05_kernel<BN, 2><<<grid, 384, smem, st>>>(ta, tb, p); break;
-        case 3: gemm_bf16_tcgen05_kernel<BN, 3><<<grid, 384, smem, st>>>(ta, tb, p); break;
-        case 4: gemm_bf16_tcgen05_kernel<BN, 4><<<grid, 384, smem, st>>>(ta, tb, p); break;
-        case 5: gemm_bf16_tcgen05_kernel<BN, 5><<<grid, 384, smem, st>>>(ta, tb, p); break;
-        case 6: gemm_bf16_tcgen05_kernel<BN, 6><<<grid, 384, smem, st>>>(ta, tb, p); break;
-        case 7: gemm_bf16_tcgen05_kernel<BN, 7><<<grid, 384, smem, st>>>(ta, tb, p); break;
-        case 8: gemm_bf16_tcgen05_kernel<BN, 8><<<grid, 384, smem, st>>>(ta, tb, p); break;
-        case 9: gemm_bf16_tcgen05_kernel<BN, 9><<<grid, 384, smem, st>>>(ta, tb, p); break;
+        case 0: CU_TRY(launch_k(gemm_bf16_tcgen05_kernel<BN, 0>, grid, 384, smem, st, ta, tb, p)); break;
+        case 1: CU_TRY(launch_k(gemm_bf16_tcgen05_kernel<BN, 1>, grid, 384, smem, st, ta, tb, p)); break;
+        case 2: CU_TRY(launch_k(gemm_bf16_tcgen05_kernel<BN, 2>, grid, 384, smem, st, ta, tb, p)); break;
+        case 3: CU_TRY(launch_k(gemm_bf16_tcgen05_kernel<BN, 3>, grid, 384, smem, st, ta, tb, p)); break;
+        case 4: CU_TRY(launch_k(gemm_bf16_tcgen05_kernel<BN, 4>, grid, 384, smem, st, ta, tb, p)); break;
+        case 5: CU_TRY(launch_k(gemm_bf16_tcgen05_kernel<BN, 5>, grid, 384, smem, st, ta, tb, p)); break;
+        case 6: CU_TRY(launch_k(gemm_bf16_tcgen05_kernel<BN, 6>, grid, 384, smem, st, ta, tb, p)); break;
+        case 7: CU_TRY(launch_k(gemm_bf16_tcgen05_kernel<BN, 7>, grid, 384, smem, st, ta, tb, p)); break;
+        case 8: CU_TRY(launch_k(gemm_bf16_tcgen05_kernel<BN, 8>, grid, 384, smem, st, ta, tb, p)); break;
+        case 9: CU_TRY(launch_k(gemm_bf16_tcgen05_kernel<BN, 9>, grid, 384, smem, st, ta, tb, p)); break;
         default: return fail(MB_ERR_INVALID, "bad epilogue %d", epi);
     }
     CU_TRY(cudaGetLastError());
@@ -769,16 +789,16 @@ static int launch_gemm2(mb_handle* h, const CUtensorMap& ta, const CUtensorMap& 
     if (tiles < pairs) pairs = tiles;
     const int grid = 2 * pairs, smem = gemm2_smem_bytes(epi);
     switch (epi) {
-        case 0: gemm2_bf16_tcgen05_kernel<0><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, tr, p); break;
-        case 1: gemm2_bf16_tcgen05_kernel<1><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, tr, p); break;
-        case 2: gemm2_bf16_tcgen05_kernel<2><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, tr, p); break;
-        case 3: gemm2_bf16_tcgen05_kernel<3><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, tr, p); break;
-        case 4: gemm2_bf16_tcgen05_kernel<4><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, tr, p); break;
-        case 5: gemm2_bf16_tcgen05_kernel<5><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, tr, p); break;
-        case 6: gemm2_bf16_tcgen05_kernel<6><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, tr, p); break;
-        case 7: gemm2_bf16_tcgen05_kernel<7><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, tr, p); break;
-        case 8: gemm2_bf16_tcgen05_kernel<8><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, tr, p); break;
-        case 9: gemm2_bf16_tcgen05_kernel<9><<<grid, Gemm2Cfg::THREADS, smem, st>>>(ta, tb, tc, tr, p); break;
+        case 0: CU_TRY(launch_k(gemm2_bf16_tcgen05_kernel<0>, grid, Gemm2Cfg::THREADS, smem, st, ta, tb, tc, tr, p)); break;
+        case 1: CU_TRY(launch_k(gemm2_bf16_tcgen05_kernel<1>, grid, Gemm2Cfg::THREADS, smem, st, ta, tb, tc, tr, p)); break;
+        case 2: CU_TRY(launch_k(gemm2_bf16_tcgen05_kernel<2>, grid, Gemm2Cfg::THREADS, smem, st, ta, tb, tc, tr, p)); break;
+        case 3: CU_TRY(launch_k(gemm2_bf16_tcgen05_kernel<3>, grid, Gemm2Cfg::THREADS, smem, st, ta, tb, tc, tr, p)); break;
+        case 4: CU_TRY(launch_k(gemm2_bf16_tcgen05_kernel<4>, grid, Gemm2Cfg::THREADS, smem, st, ta, tb, tc, tr, p)); break;
+        case 5: CU_TRY(launch_k(gemm2_bf16_tcgen05_kernel<5>, grid, Gemm2Cfg::THREADS, smem, st, ta, tb, tc, tr, p)); break;
+        case 6: CU_TRY(launch_k(gemm2_bf16_tcgen05_kernel<6>, grid, Gemm2Cfg::THREADS, smem, st, ta, tb, tc, tr, p)); break;
+        case 7: CU_TRY(launch_k(gemm2_bf16_tcgen05_kernel<7>, grid, Gemm2Cfg::THREADS, smem, st, ta, tb, tc, tr, p)); break;
+        case 8: CU_TRY(launch_k(gemm2_bf16_tcgen05_kernel<8>, grid, Gemm2Cfg::THREADS, smem, st, ta, tb, tc, tr, p)); break;
+        case 9: CU_TRY(launch_k(gemm2_bf16_tcgen05_kernel<9>, grid, Gemm2Cfg::THREADS, smem, st, ta, tb, tc, tr, p)); break;
         default: return fail(MB_ERR_INVALID, "bad epilogue %d", epi);
     }
     CU_TRY(cudaGetLastError());
@@ -864,7 +884,7 @@ static int run_attention(mb_handle* h, const CUtensorMap& tm_big, const CUtensor
         AttnTcParams p;
         p.out = out; p.n_items = n_seq * H; p.H = H; p.D = D; p.sl2 = sl2; p.trace = g_attn_trace;
         const int grid = p.n_items < num_sms ? p.n_items : num_sms;
-        attention_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM_BYTES, st>>>(tm_big, tm_row, p);
+        CU_TRY(launch_k(attention_tc_kernel, grid, ATC_THREADS, ATC_SMEM_BYTES, st, tm_big, tm_row, p));
     } else {
         attention_kernel<<<n_seq * H, ATT_THREADS, 2 * ATT_MAXS * ATT_LDS * 2, st>>>(qkv, out, S, D, H, sl2);
     }
@@ -884,11 +904,9 @@ static int forward_impl(mb_handle* h, const int64_t* tokens, int n_token_rows, c
     // y0 = input_proj(bits) | class_emb, + pos_emb  (pre-LayerNorm; first_layer's LN is folded into layer 0)
     {
         ProfScope prof(h, MB_PROF_EMBED, st);
-        embed_kernel<D><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(tokens, n_token_rows, labels, n_label_rows, drop, n_seq, c.seq_len,
-                                                                  c.codebook_splits, h->eff_bits, c.nclass, h->w_in_t, h->b_in,
-                                                                  h->class_emb, h->pos, h->yA, h->stA, LN_PARTIALS,
-                                                                  c.use_prenorm ? h->ln_first.g : nullptr, c.use_prenorm ? h->ln_first.b : nullptr,
-                                                                  h->tok_tables);
+        CU_TRY(launch_k(embed_kernel<D>, (unsigned)((M + 7) / 8), 256, 0, st, tokens, n_token_rows, labels, n_label_rows, drop, n_seq, c.seq_len,
+                        c.codebook_splits, h->eff_bits, c.nclass, h->w_in_t, h->b_in, h->class_emb, h->pos, h->yA, h->stA, (int)LN_PARTIALS,
+                        c.use_prenorm ? h->ln_first.g : nullptr, c.use_prenorm ? h->ln_first.b : nullptr, h->tok_tables));
     }
     CU_TRY(cudaGetLastError()); h->launches++;
     // pre-norm: the residual epilogues add the stream as stored (no statistics -> identity LayerNorm)
@@ -949,11 +967,11 @@ static int select_impl(mb_handle* h, const mb_select_args* a, cudaStream_t st) {
     const size_t smem = ((slots * 4 + 15) & ~15) + (size_t)slots * 8;
     ProfScope prof(h, MB_PROF_SELECT, st);
     switch (a->V) {
-        case 32: select_step_kernel<1><<<a->B, 512, smem, st>>>(p); break;
-        case 64: select_step_kernel<2><<<a->B, 512, smem, st>>>(p); break;
-        case 128: select_step_kernel<4><<<a->B, 512, smem, st>>>(p); break;
-        case 256: select_step_kernel<8><<<a->B, 512, smem, st>>>(p); break;
-        case 512: select_step_kernel<16><<<a->B, 512, smem, st>>>(p); break;
+        case 32: CU_TRY(launch_k(select_step_kernel<1>, a->B, 512, smem, st, p)); break;
+        case 64: CU_TRY(launch_k(select_step_kernel<2>, a->B, 512, smem, st, p)); break;
+        case 128: CU_TRY(launch_k(select_step_kernel<4>, a->B, 512, smem, st, p)); break;
+        case 256: CU_TRY(launch_k(select_step_kernel<8>, a->B, 512, smem, st, p)); break;
+        case 512: CU_TRY(launch_k(select_step_kernel<16>, a->B, 512, smem, st, p)); break;
         default: return fail(MB_ERR_INVALID, "select: vocabulary %d unsupported", a->V);
     }
     CU_TRY(cudaGetLastError());

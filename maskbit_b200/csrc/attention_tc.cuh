@@ -164,6 +164,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t smem0 = smem_u32(base);
+    pdl_launch_dependents();
+    pdl_wait();                                      // qkv is complete from here on
     const int n_local = p.n_items > (int)blockIdx.x ? (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     if (warp == 0) {

@@ -37,6 +37,8 @@ embed_kernel(const int64_t* __restrict__ tokens, int n_token_rows, const int64_t
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long rows = (long long)n_seq * (seq_len + 1);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");    // programmatic dependent launch (ptx.cuh): the tokens come from
+    asm volatile("griddepcontrol.wait;" ::: "memory");                 // the previous step's select kernel
     if (row >= rows) return;
     const int n = (int)(row / (seq_len + 1)), s = (int)(row - (long long)n * (seq_len + 1));
     float x[D / 32];   // row elements e = 4*(lane + 32*j) + i  (j = 0..D/128-1, i = 0..3)

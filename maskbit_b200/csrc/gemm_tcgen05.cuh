@@ -436,6 +436,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0) {
         if (elect_one()) {  // ---------------- TMA producer (elect.sync region: operands stay in uniform registers, no R2UR waterfall per issue)
@@ -598,6 +600,8 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
     cluster_sync_all();                              // barriers of both CTAs initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();                                      // the predecessor's outputs (A rows, statistics, residual) are complete from here on
 
     if (warp == W_PROD) {
         if (elect_one()) {  // ---------------- TMA producer (each CTA: its 128 A rows, its 128 of the 256 B rows)

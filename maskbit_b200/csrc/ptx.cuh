@@ -22,6 +22,15 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream is still
+// running: everything before pdl_wait() (barrier init, TMEM allocation, descriptor prefetch) overlaps the predecessor's tail and the
+// launch latency; pdl_wait() returns once the predecessor grid has completed and its memory is visible.  Without the attribute both
+// are no-ops.  Every kernel of the generator trunk calls pdl_launch_dependents() first (its successor may be scheduled as soon as SMs
+// free up) and pdl_wait() before its first access to global memory.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

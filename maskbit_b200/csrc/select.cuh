@@ -115,6 +115,8 @@ __global__ void __launch_bounds__(512) select_step_kernel(SelectParams p) {
     const int b = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int V = VPL * 32;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");    // programmatic dependent launch (ptx.cuh): the logits come from
+    asm volatile("griddepcontrol.wait;" ::: "memory");                 // the prediction-layer GEMM
 
     // num_masked of sample 0 (sampling.py:109): every CTA recounts it from the step's input tokens
     if (threadIdx.x == 0) s_count = 0;
