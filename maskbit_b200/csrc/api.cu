@@ -197,6 +197,30 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, __nv_bfloat16* __r
     size_t d = (size_t)o * taps * cin + (size_t)tap * cin + c;
     hi[d] = h; lo[d] = l;
 }
+// upsample_conv weight fp32 [Cout][Cin][3][3] -> four phase matrices [phase = py*2+px][Cout][tap = a*2+b][Cin], split bf16 hi/lo.
+// nearest x2 followed by a SAME 3x3 conv (autoencoder.py:224-225) equals, for output pixel (2y+py, 2x+px), a 2x2-tap conv over the
+// zero-padded LOW-resolution input whose tap (a, b) reads pixel (y + a + py - 1, x + b + px - 1) with the 3x3 taps that land on that
+// source pixel summed: rows {0}, {1,2} for py = 0 and {0,1}, {2} for py = 1 (columns alike).  Sums in fp32, then the split.
+__global__ void pack_conv_up4_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                     int cout, int cin) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)16 * cout * cin;
+    if (i >= total) return;
+    const int c = (int)(i % cin);
+    const int tap = (int)((i / cin) % 4);
+    const int o = (int)((i / ((size_t)4 * cin)) % cout);
+    const int phase = (int)(i / ((size_t)4 * cin * cout));
+    const int py = phase >> 1, px = phase & 1, a = tap >> 1, b = tap & 1;
+    const int ky0 = py == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), ky1 = py == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+    const int kx0 = px == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2), kx1 = px == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+    const float* wp = w + ((size_t)o * cin + c) * 9;
+    float v = 0.f;
+    for (int ky = ky0; ky <= ky1; ++ky)
+        for (int kx = kx0; kx <= kx1; ++kx) v += wp[ky * 3 + kx];
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    hi[i] = h; lo[i] = l;
+}
 // conv_in weight [C][bits][3][3] -> [tap][bit][C]
 __global__ void pack_conv_in_kernel(const float* __restrict__ w, float* __restrict__ out, int C, int bits) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -243,7 +267,8 @@ struct LNW { float* g = nullptr; float* b = nullptr; };
 struct Layer { Linear qkv, out, up, down; LNW ln1, ln2; };
 struct ConvW {
     __nv_bfloat16* hi = nullptr; __nv_bfloat16* lo = nullptr; float* bias = nullptr; int cin = 0, cout = 0, taps = 0;
-    CUtensorMap tm_hi, tm_lo;   // [cout][taps*cin], box 64 x 128
+    int phases = 1;             // 4: upsample conv folded into four 2x2-tap phase convs (taps = 4, weights [phase][cout][4*cin])
+    CUtensorMap tm_hi, tm_lo;   // [phases*cout][taps*cin], box 64 x 128
 };
 struct GNW { float* g = nullptr; float* b = nullptr; int C = 0; };
 struct ResBlockW { GNW n1, n2; ConvW c1, c2, nin; bool has_nin = false; };
@@ -303,6 +328,14 @@ struct mb_handle {
     float2* gn_box = nullptr;            // per-box GroupNorm partials written by the conv epilogue (ConvTcParams::gn_part)
     const float* gn_box_src = nullptr;   // the activation those partials describe (nullptr: none valid)
     __nv_bfloat16 *act_hi = nullptr, *act_lo = nullptr;   // zero-bordered bf16 hi / lo split of the current conv input
+    // The fields above are the CURRENT workspace set.  Batches of more than one 32-image chunk alternate between two sets on two
+    // streams of the handle's own, so that one chunk's HBM-bound passes (act_split, GroupNorm reduce, conv_in / conv_out) overlap
+    // the other chunk's tensor-bound convolutions (MASKBIT_B200_DEC_OVERLAP=0: one set, caller's stream).
+    struct DecWs { float *dx, *dt1, *dt2, *gn_scale, *gn_shift; double2* gn_partial; float2* gn_box; __nv_bfloat16 *act_hi, *act_lo; };
+    DecWs dec_ws[2] = {};
+    int dec_sets = 0;
+    cudaStream_t dstream[2] = {nullptr, nullptr};
+    cudaEvent_t dev_fork = nullptr, dev_join[2] = {nullptr, nullptr};
     std::map<std::vector<uint64_t>, CUtensorMap> tmap_cache;   // activation / output maps keyed by (pointer, shape, box)
     // per-kernel-class CUDA-event timing (mb_profile_*): pairs of events recorded around launches on the launch stream
     bool profiling = false;
@@ -382,9 +415,22 @@ static void free_sample_ws(mb_handle* h) {
     for (void* p : ps) if (p) cudaFree(p);
     h->tok_a = h->tok_b = h->pred_buf = h->combined = nullptr; h->logits_ws = nullptr; h->drop_ws = nullptr; h->cap_sample_B = 0; h->drop_layout_B = 0;
 }
+static void save_dec_ws(mb_handle* h, int s) {
+    h->dec_ws[s] = {h->dx, h->dt1, h->dt2, h->gn_scale, h->gn_shift, h->gn_partial, h->gn_box, h->act_hi, h->act_lo};
+}
+static void use_dec_ws(mb_handle* h, int s) {
+    const mb_handle::DecWs& w = h->dec_ws[s];
+    h->dx = w.dx; h->dt1 = w.dt1; h->dt2 = w.dt2; h->gn_scale = w.gn_scale; h->gn_shift = w.gn_shift; h->gn_partial = w.gn_partial;
+    h->gn_box = w.gn_box; h->act_hi = w.act_hi; h->act_lo = w.act_lo; h->gn_box_src = nullptr;
+}
 static void free_dec_ws(mb_handle* h) {
-    void* ps[] = {h->dx, h->dt1, h->dt2, h->gn_scale, h->gn_shift, h->gn_partial, h->act_hi, h->act_lo, h->gn_box};
-    for (void* p : ps) if (p) cudaFree(p);
+    for (int s = 0; s < h->dec_sets; ++s) {
+        const mb_handle::DecWs& w = h->dec_ws[s];
+        void* ps[] = {w.dx, w.dt1, w.dt2, w.gn_scale, w.gn_shift, w.gn_partial, w.act_hi, w.act_lo, w.gn_box};
+        for (void* p : ps) if (p) cudaFree(p);
+        h->dec_ws[s] = {};
+    }
+    h->dec_sets = 0;
     h->dx = h->dt1 = h->dt2 = h->gn_scale = h->gn_shift = nullptr; h->gn_partial = nullptr; h->act_hi = h->act_lo = nullptr; h->gn_box = nullptr; h->gn_box_src = nullptr;
     h->tmap_cache.clear(); h->dec_cap = 0;
 }
@@ -395,6 +441,8 @@ extern "C" void mb_destroy(mb_handle* h) {
     for (int m = 0; m < 2; ++m) for (auto& kv : h->staged[m]) cudaFree(kv.second.ptr);
     for (void* p : h->allocs) cudaFree(p);
     free_ws(h); free_sample_ws(h); free_dec_ws(h);
+    for (int i = 0; i < 2; ++i) { if (h->dstream[i]) cudaStreamDestroy(h->dstream[i]); if (h->dev_join[i]) cudaEventDestroy(h->dev_join[i]); }
+    if (h->dev_fork) cudaEventDestroy(h->dev_fork);
     if (h->gstream) cudaStreamDestroy(h->gstream);
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     if (h->ev_out) cudaEventDestroy(h->ev_out);
@@ -600,18 +648,22 @@ static int finalize_generator(mb_handle* h) {
     return 0;
 }
 
-static int make_conv(mb_handle* h, const std::string& name, int cout, int cin, int k, bool bias, ConvW* W) {
+static bool g_fold_upsample = true;   // MASKBIT_B200_FOLD_UP=0: nearest x2 by index in act_split + the plain 3x3 conv (A/B timing)
+static int make_conv(mb_handle* h, const std::string& name, int cout, int cin, int k, bool bias, ConvW* W, bool upsample = false) {
     DevTensor t;
     MB_TRY(take(h, MB_TOKENIZER, name + ".weight", {cout, cin, k, k}, &t));
     W->cin = cin; W->cout = cout; W->taps = k * k;
     if (cin % ConvTcCfg::BK || cout % ConvTcCfg::BN) return fail(MB_ERR_INVALID, "conv %s: channels %d->%d not tileable", name.c_str(), cin, cout);
-    const size_t n = (size_t)cout * cin * k * k;
+    if (const char* e = getenv("MASKBIT_B200_FOLD_UP")) g_fold_upsample = atoi(e) != 0;
+    if (upsample && k == 3 && g_fold_upsample) { W->phases = 4; W->taps = 4; }
+    const size_t n = (size_t)cout * cin * W->taps * W->phases;
     MB_TRY(dev_alloc(h, &W->hi, n));
     MB_TRY(dev_alloc(h, &W->lo, n));
-    pack_conv_kernel<<<(unsigned)((n + 255) / 256), 256>>>(t.ptr, W->hi, W->lo, cout, cin, k * k);
+    if (W->phases == 4) pack_conv_up4_kernel<<<(unsigned)((n + 255) / 256), 256>>>(t.ptr, W->hi, W->lo, cout, cin);
+    else pack_conv_kernel<<<(unsigned)((n + 255) / 256), 256>>>(t.ptr, W->hi, W->lo, cout, cin, k * k);
     CU_TRY(cudaDeviceSynchronize());
-    MB_TRY(make_tmap_bf16(&W->tm_hi, W->hi, cout, (uint64_t)k * k * cin, 128));
-    MB_TRY(make_tmap_bf16(&W->tm_lo, W->lo, cout, (uint64_t)k * k * cin, 128));
+    MB_TRY(make_tmap_bf16(&W->tm_hi, W->hi, (uint64_t)W->phases * cout, (uint64_t)W->taps * cin, 128));
+    MB_TRY(make_tmap_bf16(&W->tm_lo, W->lo, (uint64_t)W->phases * cout, (uint64_t)W->taps * cin, 128));
     cudaFree(t.ptr); h->staged[MB_TOKENIZER].erase(name + ".weight");
     if (bias) MB_TRY(keep_f32(h, MB_TOKENIZER, name + ".bias", {cout}, &W->bias));
     return 0;
@@ -659,7 +711,7 @@ static int finalize_tokenizer(mb_handle* h) {
         for (int r = 0; r < c.dec_num_res_blocks; ++r)
             MB_TRY(make_block(h, "decoder.up." + std::to_string(j) + ".res_blocks." + std::to_string(r) + ".", r == 0 ? cin : cout, cout, &st.blocks[r]));
         st.has_up = lvl > 0;
-        if (st.has_up) MB_TRY(make_conv(h, "decoder.up." + std::to_string(j) + ".upsample_conv", cout, cout, 3, true, &st.up));
+        if (st.has_up) MB_TRY(make_conv(h, "decoder.up." + std::to_string(j) + ".upsample_conv", cout, cout, 3, true, &st.up, true));
     }
     h->dec_cl = cout;
     MB_TRY(make_gn(h, "decoder.norm_out", cout, &h->norm_out));
@@ -733,10 +785,12 @@ static int set_gemm2_attr() {
 }
 // CTA-pair (cta_group::2) GEMM for every N % 256 == 0 Linear; MASKBIT_B200_GEMM_2CTA=0 selects the 1-CTA kernel (A/B timing)
 static bool g_use_2cta = true;
+static bool g_dec_overlap = true;   // decoder / encoder chunks alternate between two streams + workspace sets (see mb_handle::DecWs)
 static int init_kernel_attrs() {
     static bool done = false;
     if (done) return 0;
     if (const char* e = getenv("MASKBIT_B200_GEMM_2CTA")) g_use_2cta = atoi(e) != 0;
+    if (const char* e = getenv("MASKBIT_B200_DEC_OVERLAP")) g_dec_overlap = atoi(e) != 0;
     MB_TRY(set_gemm_attr_bn<64>()); MB_TRY(set_gemm_attr_bn<128>()); MB_TRY(set_gemm_attr_bn<256>());
     MB_TRY(set_gemm2_attr<0>()); MB_TRY(set_gemm2_attr<1>()); MB_TRY(set_gemm2_attr<2>()); MB_TRY(set_gemm2_attr<3>());
     MB_TRY(set_gemm2_attr<4>()); MB_TRY(set_gemm2_attr<5>()); MB_TRY(set_gemm2_attr<6>()); MB_TRY(set_gemm2_attr<7>());
@@ -993,10 +1047,20 @@ extern "C" int mb_combine_tokens(mb_handle* h, const int64_t* tokens, int B, int
 
 // ------------------------------------------------------------------------------------------------ decoder
 static const int kDecChunk = 32;
-static int ensure_dec_ws(mb_handle* h, int nb) {
-    if (nb <= h->dec_cap) return 0;
+static int ensure_dec_ws(mb_handle* h, int nb, int sets) {
+    if (nb <= h->dec_cap && sets <= h->dec_sets) { use_dec_ws(h, 0); return 0; }
     CU_TRY(cudaDeviceSynchronize());
+    if (sets < h->dec_sets) sets = h->dec_sets;
+    if (nb < h->dec_cap) nb = h->dec_cap;
     free_dec_ws(h);
+    if (sets > 1 && !h->dstream[0]) {
+        for (int i = 0; i < 2; ++i) {
+            CU_TRY(cudaStreamCreateWithFlags(&h->dstream[i], cudaStreamNonBlocking));
+            CU_TRY(cudaEventCreateWithFlags(&h->dev_join[i], cudaEventDisableTiming));
+        }
+        CU_TRY(cudaEventCreateWithFlags(&h->dev_fork, cudaEventDisableTiming));
+    }
+  for (int set = 0; set < sets; ++set) {
     const mb_config& c = h->cfg;
     const int P = (int)lround(sqrt((double)c.seq_len));
     size_t max_elems = 0;
@@ -1035,9 +1099,39 @@ static int ensure_dec_ws(mb_handle* h, int nb) {
     }
     MB_TRY(dev_alloc(h, &h->act_hi, max_pad * nb, false));
     MB_TRY(dev_alloc(h, &h->act_lo, max_pad * nb, false));
+    save_dec_ws(h, set);
+    h->dec_sets = set + 1;
+  }
+    use_dec_ws(h, 0);
     h->dec_cap = nb;
     return 0;
 }
+// Chunk loop of the decoder / encoder: chunk i runs on the handle's stream i & 1 with workspace set i & 1 (fork from / join into the
+// caller's stream by events), or everything on the caller's stream when there is a single chunk.
+struct ChunkStreams {
+    mb_handle* h; cudaStream_t caller; bool split; int used = 0;
+    ChunkStreams(mb_handle* h_, cudaStream_t st, int chunks) : h(h_), caller(st), split(chunks > 1 && g_dec_overlap && h_->dec_sets > 1 && !h_->profiling) {}
+    int begin() {
+        if (!split) return 0;
+        CU_TRY(cudaEventRecord(h->dev_fork, caller));
+        for (int i = 0; i < 2; ++i) CU_TRY(cudaStreamWaitEvent(h->dstream[i], h->dev_fork, 0));
+        return 0;
+    }
+    cudaStream_t stream_for(int chunk) {
+        if (!split) { use_dec_ws(h, 0); return caller; }
+        use_dec_ws(h, chunk & 1);
+        return h->dstream[chunk & 1];
+    }
+    int end() {
+        use_dec_ws(h, 0);
+        if (!split) return 0;
+        for (int i = 0; i < 2; ++i) {
+            CU_TRY(cudaEventRecord(h->dev_join[i], h->dstream[i]));
+            CU_TRY(cudaStreamWaitEvent(caller, h->dev_join[i], 0));
+        }
+        return 0;
+    }
+};
 
 static int run_gn(mb_handle* h, const float* x, const GNW& g, int nb, int R, cudaStream_t st) {
     const int HW = R * R;
@@ -1068,11 +1162,48 @@ static int cached_tmap(mb_handle* h, CUtensorMap** out, CUtensorMapDataType dt, 
     *out = &it->second;
     return 0;
 }
+// nearest x2 + conv3x3 as four phase convs over the low-resolution input (ConvTcParams::phases); R = OUTPUT resolution
+static int run_conv_up4(mb_handle* h, const float* in, float* out, const ConvW& w, int nb, int R, cudaStream_t st) {
+    const int Rl = R / 2;
+    if (Rl < 16) return fail(MB_ERR_INVALID, "upsample conv input resolution %d unsupported", Rl);
+    {
+        ProfScope prof(h, MB_PROF_DEC_IO, st);
+        const dim3 agrid((unsigned)(((Rl + 2) * (w.cin / 8) + 255) / 256), (unsigned)(nb * (Rl + 2)));
+        act_split_kernel<<<agrid, 256, 0, st>>>(in, nullptr, nullptr, h->act_hi, h->act_lo, nb, Rl, Rl, w.cin, 0, 1);
+        CU_TRY(cudaGetLastError()); h->launches++;
+    }
+    ConvTcParams p;
+    p.n_img = nb; p.H = Rl; p.W = Rl; p.Cin = w.cin; p.Cout = w.cout; p.taps = 4; p.stride = 1; p.phases = 4;
+    p.bw = Rl >= 128 ? 128 : Rl; p.bh = 128 / p.bw;
+    p.bias = w.bias; p.residual = nullptr;
+    const int cpg = w.cout / 32;
+    const bool fuse_gn = cpg == 4 || cpg == 8 || cpg == 16;
+    p.gn_part = fuse_gn ? h->gn_box : nullptr;
+    p.gn_cpg_log2 = cpg == 4 ? 2 : (cpg == 8 ? 3 : 4);
+    h->gn_box_src = fuse_gn ? out : nullptr;
+    const uint64_t adims[5] = {(uint64_t)w.cin, (uint64_t)Rl + 2, (uint64_t)Rl + 2, (uint64_t)nb, 1u};
+    const uint32_t abox[5] = {64, (uint32_t)p.bw, (uint32_t)p.bh, 1, 1};
+    // output [nb, R, R, C] viewed as {C, px, x, py, n*Rl + y}: a warp's 32 low-resolution pixels are one strided box
+    const uint32_t bx = p.bw < 32 ? (uint32_t)p.bw : 32u;
+    const uint64_t odims[5] = {(uint64_t)w.cout, 2u, (uint64_t)Rl, 2u, (uint64_t)nb * Rl};
+    const uint32_t obox[5] = {32, 1, bx, 1, 32 / bx};
+    CUtensorMap *tahi, *talo, *tout;
+    MB_TRY(cached_tmap(h, &tahi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 5, h->act_hi, adims, abox));
+    MB_TRY(cached_tmap(h, &talo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 5, h->act_lo, adims, abox));
+    MB_TRY(cached_tmap(h, &tout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 5, out, odims, obox));
+    const int tiles = nb * (Rl / p.bh) * (Rl / p.bw) * (w.cout / ConvTcCfg::BN) * 4;
+    const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+    ProfScope prof(h, MB_PROF_DEC_CONV, st);
+    conv_tcgen05_kernel<<<grid, 384, ConvTcCfg::SMEM_BYTES, st>>>(*tahi, *talo, w.tm_hi, w.tm_lo, *tout, p);
+    CU_TRY(cudaGetLastError()); h->launches++;
+    return 0;
+}
 // out = conv(act(in)) (+bias) (+residual): act = GroupNorm-apply + SiLU when gn, nearest x2 upsample when up (autoencoder.py:85-96,224-225)
 // R = OUTPUT resolution; stride 2 (encoder down convs, Conv2dSame pad 0/1, autoencoder.py:7-36,160) reads its input at 2R.
 static int run_conv(mb_handle* h, const float* in, float* out, const ConvW& w, int nb, int R, bool gn, int up, const float* residual,
                     cudaStream_t st, int stride = 1) {
     if (R < 16 || (R & (R - 1))) return fail(MB_ERR_INVALID, "conv resolution %d unsupported (power of two >= 16)", R);
+    if (up && w.phases == 4) return run_conv_up4(h, in, out, w, nb, R, st);
     const int Rin = R * stride;                                     // size of the (upsampled) conv input
     {
         ProfScope prof(h, MB_PROF_DEC_IO, st);
@@ -1082,7 +1213,7 @@ static int run_conv(mb_handle* h, const float* in, float* out, const ConvW& w, i
         CU_TRY(cudaGetLastError()); h->launches++;
     }
     ConvTcParams p;
-    p.n_img = nb; p.H = R; p.W = R; p.Cin = w.cin; p.Cout = w.cout; p.taps = w.taps; p.stride = stride;
+    p.n_img = nb; p.H = R; p.W = R; p.Cin = w.cin; p.Cout = w.cout; p.taps = w.taps; p.stride = stride; p.phases = 1;
     p.bw = R >= 128 ? 128 : R; p.bh = 128 / p.bw;
     p.bias = w.bias; p.residual = residual;
     // GroupNorm partials of the output for whichever GroupNorm reads it next (32 groups of Cout / 32 = 4, 8 or 16 channels)
@@ -1121,14 +1252,17 @@ static int run_block(mb_handle* h, const ResBlockW& rb, float*& X, float*& T1, f
     return 0;
 }
 
-static int decode_impl(mb_handle* h, const int64_t* tokens, int B, float* images, cudaStream_t st) {
+static int decode_impl(mb_handle* h, const int64_t* tokens, int B, float* images, cudaStream_t caller_st) {
     if (!h->finalized[MB_TOKENIZER]) return fail(MB_ERR_STATE, "tokenizer weights not loaded (mb_set_tensor + mb_finalize)");
     const mb_config& c = h->cfg;
     const int P = (int)lround(sqrt((double)c.seq_len));
     if (P * P != c.seq_len) return fail(MB_ERR_INVALID, "seq_len %d is not a square", c.seq_len);
-    MB_TRY(ensure_dec_ws(h, B < kDecChunk ? B : kDecChunk));
+    MB_TRY(ensure_dec_ws(h, B < kDecChunk ? B : kDecChunk, B > kDecChunk && g_dec_overlap ? 2 : 1));
+    ChunkStreams cs(h, caller_st, (B + kDecChunk - 1) / kDecChunk);
+    MB_TRY(cs.begin());
     for (int b0 = 0; b0 < B; b0 += kDecChunk) {
         const int nb = B - b0 < kDecChunk ? B - b0 : kDecChunk;
+        cudaStream_t st = cs.stream_for(b0 / kDecChunk);
         float *X = h->dx, *T1 = h->dt1, *T2 = h->dt2;
         int R = P;
         h->gn_box_src = nullptr;                                   // conv_in_tokens_kernel writes X without partials
@@ -1151,7 +1285,7 @@ static int decode_impl(mb_handle* h, const int64_t* tokens, int B, float* images
         conv_out_kernel<<<grid, 256, 0, st>>>(X, h->gn_scale, h->gn_shift, h->cout_w, h->cout_b, images + (size_t)b0 * 3 * R * R, R, R, h->dec_cl); }
         CU_TRY(cudaGetLastError()); h->launches++;
     }
-    return 0;
+    return cs.end();
 }
 extern "C" int mb_decode_tokens(mb_handle* h, const int64_t* tokens, int B, float* images, mb_stream stream) {
     if (!h || !tokens || !images || B <= 0) return fail(MB_ERR_INVALID, "mb_decode_tokens: bad argument");
@@ -1160,14 +1294,17 @@ extern "C" int mb_decode_tokens(mb_handle* h, const int64_t* tokens, int B, floa
 
 // ConvVQModel.encode (conv_vqgan.py:71-84): ConvEncoder (autoencoder.py:268-286) + LookupFreeQuantizer sign / index
 // (lookup_free.py:56-62).  images fp32 NCHW [B,3,H,W] -> z fp32 NCHW [B,bits,P,P] (optional), indices int64 [B,P*P] (optional)
-static int encode_impl(mb_handle* h, const float* images, int B, float* z, int64_t* indices, cudaStream_t st) {
+static int encode_impl(mb_handle* h, const float* images, int B, float* z, int64_t* indices, cudaStream_t caller_st) {
     if (!h->finalized[MB_TOKENIZER]) return fail(MB_ERR_STATE, "tokenizer weights not loaded (mb_set_tensor + mb_finalize)");
     const mb_config& c = h->cfg;
     const int P = (int)lround(sqrt((double)c.seq_len));
     const int Rimg = P << (c.dec_num_resolutions - 1);
-    MB_TRY(ensure_dec_ws(h, B < kDecChunk ? B : kDecChunk));
+    MB_TRY(ensure_dec_ws(h, B < kDecChunk ? B : kDecChunk, B > kDecChunk && g_dec_overlap ? 2 : 1));
+    ChunkStreams cs(h, caller_st, (B + kDecChunk - 1) / kDecChunk);
+    MB_TRY(cs.begin());
     for (int b0 = 0; b0 < B; b0 += kDecChunk) {
         const int nb = B - b0 < kDecChunk ? B - b0 : kDecChunk;
+        cudaStream_t st = cs.stream_for(b0 / kDecChunk);
         float *X = h->dx, *T1 = h->dt1, *T2 = h->dt2;
         int R = Rimg;
         h->gn_box_src = nullptr;                                   // enc_conv_in_kernel writes X without partials
@@ -1198,7 +1335,7 @@ static int encode_impl(mb_handle* h, const float* images, int B, float* z, int64
             CU_TRY(cudaGetLastError()); h->launches++;
         }
     }
-    return 0;
+    return cs.end();
 }
 extern "C" int mb_encode(mb_handle* h, const float* images, int B, float* z, int64_t* indices, mb_stream stream) {
     if (!h || !images || B <= 0 || (!z && !indices)) return fail(MB_ERR_INVALID, "mb_encode: bad argument");

@@ -80,6 +80,11 @@ act_split_kernel(const float* __restrict__ in, const float* __restrict__ scale, 
 struct ConvTcParams {
     int n_img, H, W, Cin, Cout, taps;   // H, W = OUTPUT size; taps = 9 (3x3) or 1 (1x1)
     int stride;                         // 1, or 2 (3x3 only; input stored as 4 parity planes)
+    int phases;                         // 1, or 4: nearest-x2 upsample folded into the conv (autoencoder.py:224-225).  H, W are then
+                                        // the LOW-resolution size; output pixel (2y+py, 2x+px) of phase (py, px) is a 2x2-tap conv
+                                        // over the low-resolution input with pre-summed weights (taps = 4, tap (a, b) reads padded
+                                        // pixel (y + a + py, x + b + px)): 16 instead of 36 tap-products per 2x2 output pixels.
+                                        // Weights [phase][Cout][4*Cin]; tm_out is the 5-D view {C, px, W, py, n*H + y} of the output
     int bw, bh;                         // pixel tile = bh rows x bw columns, bw * bh = 128
     const float* bias;                  // [Cout] or nullptr
     const float* residual;              // fp32 NHWC [n_img*H*W, Cout] or nullptr
@@ -122,7 +127,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
     const int tiles_x = p.W / p.bw, tiles_y = p.H / p.bh;
     const int pix_tiles = p.n_img * tiles_y * tiles_x;
     const int num_n = p.Cout / BN;
-    const int num_tiles = pix_tiles * num_n;
+    const int num_np = num_n * p.phases;                 // tiles sharing one input pixel tile are consecutive
+    const int num_tiles = pix_tiles * num_np;
     const int kchunks = p.Cin / C::BK;
     const int num_k = p.taps * kchunks;
 
@@ -145,9 +151,11 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
         if (elect_one()) {  // ---------------- TMA producer
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int pt = tile / num_n, n_blk = tile - pt * num_n;
+                const int pt = tile / num_np, rem = tile - pt * num_np;
+                const int uph = rem / num_n, n_blk = rem - uph * num_n;
                 const int xb = pt % tiles_x, yb = (pt / tiles_x) % tiles_y, img = pt / (tiles_x * tiles_y);
                 const int x0 = xb * p.bw, y0 = yb * p.bh;
+                const int wrow = uph * p.Cout + n_blk * BN;
                 for (int kb = 0; kb < num_k; ++kb) {
                     const int tap = kb / kchunks, c0 = (kb - tap * kchunks) * C::BK;
                     // stride 1, 3x3: padded input pixel of output (y, x) under tap (dy, dx) is (y + dy, x + dx), dy, dx in 0..2;
@@ -156,13 +164,14 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
                     //           (y + (dy+1)/2, x + (dx+1)/2)
                     int dy = p.taps == 9 ? tap / 3 : 1, dx = p.taps == 9 ? tap % 3 : 1, plane = 0;
                     if (p.stride == 2) { plane = ((dy + 1) & 1) * 2 + ((dx + 1) & 1); dy = (dy + 1) >> 1; dx = (dx + 1) >> 1; }
+                    if (p.phases == 4) { dy = (tap >> 1) + (uph >> 1); dx = (tap & 1) + (uph & 1); }
                     uint8_t* sb = base + stage * C::STAGE_BYTES;
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
                     tma_load_5d(sb, &tm_ahi, &full[stage], c0, x0 + dx, y0 + dy, img, plane);
                     tma_load_5d(sb + C::TILE_BYTES, &tm_alo, &full[stage], c0, x0 + dx, y0 + dy, img, plane);
-                    tma_load_2d(sb + 2 * C::TILE_BYTES, &tm_whi, &full[stage], tap * p.Cin + c0, n_blk * BN);
-                    tma_load_2d(sb + 3 * C::TILE_BYTES, &tm_wlo, &full[stage], tap * p.Cin + c0, n_blk * BN);
+                    tma_load_2d(sb + 2 * C::TILE_BYTES, &tm_whi, &full[stage], tap * p.Cin + c0, wrow);
+                    tma_load_2d(sb + 3 * C::TILE_BYTES, &tm_wlo, &full[stage], tap * p.Cin + c0, wrow);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -199,10 +208,15 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
         uint8_t* stg = smem_stg + (warp - 4) * 4096;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int pt = tile / num_n, n_blk = tile - pt * num_n;
+            const int pt = tile / num_np, rem = tile - pt * num_np;
+            const int uph = rem / num_n, n_blk = rem - uph * num_n;
             const uint32_t as = it & 1, aphase = (it >> 1) & 1;
             const long long row0 = (long long)pt * 128 + quarter * 32;     // tiles enumerate pixels in NHWC order
             const long long row = row0 + lane;
+            // phases == 4: this warp's 32 low-resolution pixels (one row segment, or two 16-pixel rows) and its statistics slot
+            const int tpi = tiles_x * tiles_y, img = pt / tpi, pti = pt - img * tpi;
+            const int px0 = (pti % tiles_x) * p.bw + (quarter * 32) % p.bw, py0 = (pti / tiles_x) * p.bh + (quarter * 32) / p.bw;
+            const long long gn_slot = p.phases == 4 ? ((long long)(img * 4 + uph) * tpi + pti) * 4 + quarter : (row0 >> 5);
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
 #pragma unroll 1
@@ -239,7 +253,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
                 fence_async_proxy();
                 __syncwarp();
                 if (elect_one()) {
-                    tma_store_2d(&tm_out, stg, n0, (int)row0);
+                    if (p.phases == 4) tma_store_5d(&tm_out, stg, n0, uph & 1, px0, uph >> 1, img * p.H + py0);
+                    else tma_store_2d(&tm_out, stg, n0, (int)row0);
                     tma_store_commit();
                 }
                 if (p.gn_part) {
@@ -258,7 +273,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
                         s2 += __shfl_xor_sync(0xffffffffu, s2, o);
                     }
                     if ((lane & ((1 << p.gn_cpg_log2) - 1)) == 0)
-                        p.gn_part[(size_t)(row0 >> 5) * 32 + ((n0 + lane) >> p.gn_cpg_log2)] = make_float2(s1, s2);
+                        p.gn_part[(size_t)gn_slot * 32 + ((n0 + lane) >> p.gn_cpg_log2)] = make_float2(s1, s2);
                 }
             }
             tc_fence_before();
