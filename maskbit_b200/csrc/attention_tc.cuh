@@ -25,6 +25,7 @@
 // Input  qkv  bf16 [rows, 3*D] through two TMA maps (box 64x256 and box 64x16); head h at columns h*64 of each third
 // Output out  bf16 [n_seq*257, D] (one 128-byte row segment per thread, 256-bit stores)
 #pragma once
+#include <type_traits>
 #include "attention.cuh"   // ldsm_x4, ldsm_x4_t, mma_bf16_16816
 #include "ptx.cuh"
 
@@ -47,6 +48,19 @@
                             // 3-input-max pass 1 it is 4 % faster, 0.374 vs 0.389 ms, and 1.3 % less energy per launch: tools/kpower.py)
 #endif
 
+#ifndef ATC_POLY
+#define ATC_POLY 0          // of every 16 exponential pairs in pass 2, this many are evaluated on the FMA pipe (round-to-nearest range
+                            // reduction + degree-3 polynomial + exponent insert) instead of MUFU.EX2: the MUFU pipe (16 / clk / SM) is
+                            // the floor of pass 2 (4.1 k clk per item); P is rounded to bf16 afterwards, the polynomial's 7.5e-5 is invisible
+#endif
+#ifndef ATC_FASTMAX
+#define ATC_FASTMAX 0       // 1: no row-max pass.  Softmax is shift-invariant and P (bf16) / the row sum / O (fp32) have the fp32 exponent
+                            // range, so any shift within ~2^100 of the true maximum gives the same result: rows are shifted by their
+                            // class-key score s256 (already in a register).  A row whose sum overflows (maximum more than ~88 nats above
+                            // its class-key logit) flags its item; flagged items are redone by the same CTA with the exact row maximum
+                            // after its main loop (second round below), so the result never depends on the estimate.
+#endif
+
 namespace mb {
 
 constexpr int ATC_THREADS = 384;
@@ -55,7 +69,9 @@ constexpr int ATC_ROW_BYTES = 16 * 128;               // 16-row box holding the 
 constexpr int ATC_STAGE_BYTES = 3 * ATC_TILE_BYTES + 3 * ATC_ROW_BYTES;
 constexpr int ATC_SCLS_BYTES = 2 * 256 * 4;           // class-query scores against the 256 tile keys, per stage
 constexpr int ATC_PCLS_BYTES = 576;                   // class-query probabilities, bf16 [272] (keys 257.. = 0)
-constexpr int ATC_SMEM_BYTES = 2 * ATC_STAGE_BYTES + ATC_SCLS_BYTES + ATC_PCLS_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int ATC_RETRY_CAP = 1024;                   // local items per CTA that the fast-max round can flag (more: exact from the start)
+constexpr int ATC_RETRY_BYTES = ATC_RETRY_CAP / 8 + ATC_RETRY_CAP * 2 + 16;   // bit mask + compacted list (uint16) + count
+constexpr int ATC_SMEM_BYTES = 2 * ATC_STAGE_BYTES + ATC_SCLS_BYTES + ATC_PCLS_BYTES + 1024 /*align*/ + 256 /*barriers*/ + ATC_RETRY_BYTES;
 
 // D[tmem] (+)= A[tmem] * B[smem]
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -100,6 +116,24 @@ __device__ __forceinline__ float fast_exp2(float x) {   // MUFU.EX2; arguments h
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+// exp2 of a pair on the FMA pipe: x = n + f with n = round(x) (magic-number add), f in [-0.5, 0.5]; 2^f by a degree-3 minimax
+// polynomial (7.5e-5 relative); 2^n inserted by adding n to the exponent field.  Valid for x in [-126, 127].
+__device__ __forceinline__ void exp2_poly2(float& x0, float& x1) {
+    constexpr float MAGIC = 12582912.0f;                 // 1.5 * 2^23: the integer lands in the low mantissa bits
+    x0 = fmaxf(x0, -126.0f); x1 = fmaxf(x1, -126.0f);
+#if ATC_FASTMAX
+    x0 = fminf(x0, 128.0f); x1 = fminf(x1, 128.0f);      // 2^128 -> exponent field 255: inf / NaN, caught by the row-sum check
+#endif
+    float t0, t1, n0, n1, f0, f1, p0, p1;
+    fadd2(t0, t1, x0, x1, MAGIC, MAGIC);
+    fadd2(n0, n1, t0, t1, -MAGIC, -MAGIC);
+    ffma2(f0, f1, n0, n1, -1.0f, -1.0f, x0, x1);
+    ffma2(p0, p1, f0, f1, 0.0551716685f, 0.0551716685f, 0.242611125f, 0.242611125f);
+    ffma2(p0, p1, p0, p1, f0, f1, 0.693260968f, 0.693260968f);
+    ffma2(p0, p1, p0, p1, f0, f1, 0.999928057f, 0.999928057f);
+    x0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+    x1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 // three-input maximum (FMNMX3 on sm_100): the row-max pass needs one instruction per two scores
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
@@ -147,6 +181,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
     uint64_t* t_free = bars + 14;    // [2] TMEM region t drained by the epilogue (4 warps)
     uint64_t* scls_ready = bars + 16;// [2] scls[stage] written by the 8 softmax warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    uint32_t* retry_mask = reinterpret_cast<uint32_t*>(bars + 32);                               // [ATC_RETRY_CAP / 32]
+    uint16_t* retry_list = reinterpret_cast<uint16_t*>(retry_mask + ATC_RETRY_CAP / 32);         // [ATC_RETRY_CAP]
+    int* retry_count = reinterpret_cast<int*>(retry_list + ATC_RETRY_CAP);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_big); tma_prefetch_desc(&tm_row); }
@@ -158,6 +195,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
         }
         fence_mbar_init();
     }
+    if (warp == 2 && lane < ATC_RETRY_CAP / 32) retry_mask[lane] = 0;
     if (warp == 3) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
@@ -167,13 +205,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
     pdl_launch_dependents();
     pdl_wait();                                      // qkv is complete from here on
     const int n_local = p.n_items > (int)blockIdx.x ? (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    // Processed-item sequence of this CTA: k in [0, n_local) is local item k; with ATC_FASTMAX a second round
+    // k in [n_local, n_local + n_retry) redoes the flagged local items retry_list[k - n_local] with the exact row maximum.
+    // Every role runs the same sequence; k is also the running index all barrier parities and stage slots derive from.
+    const bool fast_round = ATC_FASTMAX && n_local <= ATC_RETRY_CAP;
+    int n_retry = 0;
+    auto item_of = [&](int k) -> int { return (int)blockIdx.x + (k < n_local ? k : (int)retry_list[k - n_local]) * (int)gridDim.x; };
+#pragma unroll 1
+  for (int round = 0; round < (ATC_FASTMAX ? 2 : 1); ++round) {
+    const int k0 = round ? n_local : 0, k1 = round ? n_local + n_retry : n_local;
+    const bool exact = round != 0 || !fast_round;
+    (void)exact; (void)retry_count;
 
     if (warp == 0) {
         if (elect_one()) {  // -------------------------------------------------------------- TMA producer
             // (elect.sync region, here and in the MMA issuers: the compiler keeps descriptors and addresses in uniform registers;
             //  under `lane == 0` every UTMALDG / UTCHMMA was wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop, ~150 clk each)
-            uint32_t it = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+            for (int it = k0; it < k1; ++it) {
+                const int item = item_of(it);
                 const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
                 const int seq = item / p.H, head = item - seq * p.H;
                 const int row0 = seq * S, col = head * 64;
@@ -199,7 +248,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
             constexpr uint32_t idesc_o = make_idesc(1, 128, 64) | (1u << 16);   // B (= V) is MN-major
             const int t = warp - 1;
             const uint32_t tr = tmem_base + t * 256;
-            for (int it = 0; it < n_local; ++it) {
+            for (int it = k0; it < k1; ++it) {
                 const int st = it & 1;
                 const uint32_t sq = smem0 + st * ATC_STAGE_BYTES, sk = sq + ATC_TILE_BYTES, sv = sk + ATC_TILE_BYTES;
                 mbar_wait(&fullqk[st], (it >> 1) & 1);
@@ -231,10 +280,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
             }
         }
     } else if (warp == 3) {  // -------------------------------------------------------------- the class-token query row
-        uint32_t it = 0;
         const int g = lane >> 2, t4 = lane & 3;
         const uint32_t pcls_a = smem_u32(pcls);
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        for (int it = k0; it < k1; ++it) {
+            const int item = item_of(it);
             const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
             const int seq = item / p.H, head = item - seq * p.H;
             const uint32_t sq = smem0 + st * ATC_STAGE_BYTES, sv = sq + 2 * ATC_TILE_BYTES;
@@ -307,7 +356,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
         const int row = t * 128 + quarter * 32 + lane;                 // query row inside the sequence (0..255)
         const uint32_t treg = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * 256;
 #if ATC_PINGPONG
-        if (t == 1) named_bar_arrive(1, 256);                          // warpgroup 0 takes the first turn in pass 2
+        if (t == 1 && round == 0) named_bar_arrive(1, 256);            // warpgroup 0 takes the first turn in pass 2 (the hand-over
+                                                                       // after a round's last item is the first turn of the next round)
 #endif
         // ---- the 257th column and row for this warp's 32 query rows / 32 keys (rows base .. base+31 of the Q and K tiles of local
         // item `j`): m16n8k16 tiles with the class-token vector as the single live column of B.  Returns s256 of this thread's row.
@@ -351,9 +401,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
             const float v10 = __shfl_sync(0xffffffffu, ccol[1][0], src), v12 = __shfl_sync(0xffffffffu, ccol[1][2], src);
             return (lane & 16) ? ((lane & 8) ? v12 : v10) : ((lane & 8) ? v02 : v00);
         };
-        float s256 = n_local > 0 ? class_pass(0) : 0.f;
-        uint32_t it = 0;
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        // The item loop exists once per mode (exact row maximum / class-key shift): as a run-time flag the exact pass was
+        // if-converted into ~300 predicated-off instructions per item and the "fast" round ran 38 % SLOWER than the exact kernel.
+        auto item_loop = [&](auto exact_c) {
+        constexpr bool kExact = decltype(exact_c)::value;
+        float s256 = k1 > k0 ? class_pass(k0) : 0.f;
+        for (int it = k0; it < k1; ++it) {
+            const int item = item_of(it);
             const int st = it & 1; const uint32_t ph = (it >> 1) & 1, ip = it & 1;
             const int seq = item / p.H, head = item - seq * p.H;
             const uint32_t vc = smem0 + st * ATC_STAGE_BYTES + 3 * ATC_TILE_BYTES + 2 * ATC_ROW_BYTES;
@@ -362,20 +416,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
             if (quarter == 0 && lane == 0) ATC_EV(3 + t, 0, it);
             float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             uint32_t va[32], vb[32];
-            // pass 1: row max over keys 0..255.  The load of chunk c+1 is in flight while chunk c is reduced.
             tmem_ld_32x32(treg, va);
             tmem_ld_wait();
+            if constexpr (kExact) {
+                // pass 1: row max over keys 0..255.  The load of chunk c+1 is in flight while chunk c is reduced.
 #pragma unroll
-            for (int c = 0; c < 8; c += 2) {
-                tmem_ld_32x32(treg + (c + 1) * 32, vb);
+                for (int c = 0; c < 8; c += 2) {
+                    tmem_ld_32x32(treg + (c + 1) * 32, vb);
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) m4[(j >> 1) & 3] = fmax3(m4[(j >> 1) & 3], __uint_as_float(va[j]), __uint_as_float(va[j + 1]));
-                tmem_ld_wait();
-                tmem_ld_32x32(treg + ((c + 2) & 7) * 32, va);      // wraps to chunk 0: first chunk of pass 2
+                    for (int j = 0; j < 32; j += 2) m4[(j >> 1) & 3] = fmax3(m4[(j >> 1) & 3], __uint_as_float(va[j]), __uint_as_float(va[j + 1]));
+                    tmem_ld_wait();
+                    tmem_ld_32x32(treg + ((c + 2) & 7) * 32, va);      // wraps to chunk 0: first chunk of pass 2
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) m4[(j >> 1) & 3] = fmax3(m4[(j >> 1) & 3], __uint_as_float(vb[j]), __uint_as_float(vb[j + 1]));
-                tmem_ld_wait();
+                    for (int j = 0; j < 32; j += 2) m4[(j >> 1) & 3] = fmax3(m4[(j >> 1) & 3], __uint_as_float(vb[j]), __uint_as_float(vb[j + 1]));
+                    tmem_ld_wait();
+                }
             }
+            // (fast round: the shift is the class-key score alone -- see ATC_FASTMAX)
             const float nms = -fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])), s256) * p.sl2;
             if (quarter == 0 && lane == 0) ATC_EV(3 + t, 1, it);
 
@@ -390,7 +447,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
                 for (int j = 0; j < 16; ++j) {
                     float x0, x1;
                     ffma2(x0, x1, __uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), p.sl2, p.sl2, nms, nms);
-                    x0 = fast_exp2(x0); x1 = fast_exp2(x1);
+                    if (ATC_POLY > 0 && ((j * ATC_POLY) & 15) < ATC_POLY) exp2_poly2(x0, x1);
+                    else { x0 = fast_exp2(x0); x1 = fast_exp2(x1); }
                     fadd2(sum0, sum1, sum0, sum1, x0, x1);
                     pk[j] = pack2_bf16(x0, x1);
                 }
@@ -413,7 +471,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[t]);
             if (quarter == 0 && lane == 0) ATC_EV(3 + t, 2, it);
-            const float s256_next = (int)it + 1 < n_local ? class_pass(it + 1) : 0.f;   // while this item's P V MMAs run
+#if ATC_FASTMAX
+            if constexpr (!kExact) {   // a row whose sum left the fp32 range (or met an inf / NaN) was shifted too little: redo the item exactly
+                const bool bad = !(sum0 + sum1 < 1e30f);
+                if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&retry_mask[it >> 5], 1u << (it & 31));
+            }
+#endif
+            const float s256_next = it + 1 < k1 ? class_pass(it + 1) : 0.f;   // while this item's P V MMAs run
             // epilogue: (O + p256 * V[256]) / (l + p256) -> bf16 row
             const float e256 = fast_exp2(fmaf(s256, p.sl2, nms));
             const float inv = 1.0f / (sum0 + sum1 + e256);
@@ -456,7 +520,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
             if (quarter == 0 && lane == 0) ATC_EV(3 + t, 4, it);
             s256 = s256_next;
         }
+        };
+#if ATC_FASTMAX
+        if (exact) item_loop(std::true_type{}); else item_loop(std::false_type{});
+#else
+        item_loop(std::true_type{});
+#endif
     }
+#if ATC_FASTMAX
+    if (round == 0) {       // compact the flagged items (normally none) into the second round's sequence
+        __syncwarp();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int n = 0;
+            for (int w = 0; w < ATC_RETRY_CAP / 32; ++w)
+                for (uint32_t m = retry_mask[w]; m; m &= m - 1) retry_list[n++] = (uint16_t)(w * 32 + __ffs(m) - 1);
+            *retry_count = n;
+        }
+        __syncthreads();
+        n_retry = fast_round ? *retry_count : 0;
+    }
+#endif
+  }
     __syncwarp();
     tc_fence_before();
     __syncthreads();
