@@ -69,6 +69,20 @@ static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     cfg.attrs = attr; cfg.numAttrs = use_pdl() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
+// the same with a run-time thread-block cluster of `cluster` CTAs along x (grid.x a multiple of it)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, unsigned cluster,
+                                    Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = use_pdl() ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ------------------------------------------------------------------------------------------------ TMA descriptors
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -274,8 +288,11 @@ struct GNW { float* g = nullptr; float* b = nullptr; int C = 0; };
 struct ResBlockW { GNW n1, n2; ConvW c1, c2, nin; bool has_nin = false; };
 struct StageW { std::vector<ResBlockW> blocks; bool has_up = false; ConvW up; };
 
+struct SplitK { float* ws = nullptr; int* cnt = nullptr; int pairs = 0; };
 struct mb_handle {
     mb_config cfg;
+    SplitK splitk;
+    const struct Linear* prefetch_next = nullptr;   // the Linear that runs after the next run_linear (its weights are prefetched into L2)
     int device = 0, num_sms = 148;
     int64_t launches = 0;
     std::map<std::string, DevTensor> staged[2];
@@ -441,6 +458,8 @@ extern "C" void mb_destroy(mb_handle* h) {
     for (int m = 0; m < 2; ++m) for (auto& kv : h->staged[m]) cudaFree(kv.second.ptr);
     for (void* p : h->allocs) cudaFree(p);
     free_ws(h); free_sample_ws(h); free_dec_ws(h);
+    if (h->splitk.ws) cudaFree(h->splitk.ws);
+    if (h->splitk.cnt) cudaFree(h->splitk.cnt);
     for (int i = 0; i < 2; ++i) { if (h->dstream[i]) cudaStreamDestroy(h->dstream[i]); if (h->dev_join[i]) cudaEventDestroy(h->dev_join[i]); }
     if (h->dev_fork) cudaEventDestroy(h->dev_fork);
     if (h->gstream) cudaStreamDestroy(h->gstream);
@@ -802,11 +821,13 @@ static int init_kernel_attrs() {
     return 0;
 }
 
+static int ensure_splitk(SplitK& sk, int pairs);
 extern "C" int mb_finalize(mb_handle* h, int model) {
     if (!h || model < 0 || model > 1) return fail(MB_ERR_INVALID, "mb_finalize: bad argument");
     if (h->finalized[model]) return fail(MB_ERR_STATE, "model %d already finalized", model);
     MB_TRY(init_kernel_attrs());
     MB_TRY(model == MB_GENERATOR ? finalize_generator(h) : finalize_tokenizer(h));
+    if (model == MB_GENERATOR) MB_TRY(ensure_splitk(h->splitk, h->num_sms / 2));
     CU_TRY(cudaDeviceSynchronize());
     h->finalized[model] = true;
     return 0;
@@ -836,11 +857,51 @@ static int launch_gemm_bn(mb_handle* h, const CUtensorMap& ta, const CUtensorMap
     if (h) h->launches++;
     return 0;
 }
+// Split-K scratch of the CTA-pair kernel (GemmParams::ksplit), sized for one unit per CTA pair: one per handle (allocated when the
+// generator is finalized, so never inside a stream capture) and a process-wide one for the handle-less test hooks.
+// GEMMs sharing a scratch must not overlap in time (a handle's forwards are stream-ordered).
+// OFF by default (MASKBIT_B200_SPLITK=1 turns it on): correct (kernel tests green with it on) but slower than the un-split schedule at
+// batch 1 -- down-projection 30 -> 70 us, out-projection 17 -> 52 us (profiles/r02_splitk_rejected.txt): the fix-up is a chain of
+// L2 round trips per warp.  What helps that corner is the L2 prefetch by idle pairs (GemmParams::prefetch).
+static SplitK g_splitk;
+static int g_splitk_on = -1;
+static int ensure_splitk(SplitK& sk, int pairs) {
+    if (g_splitk_on < 0) { const char* e = getenv("MASKBIT_B200_SPLITK"); g_splitk_on = e ? atoi(e) != 0 : 0; }
+    if (!g_splitk_on || pairs <= sk.pairs) return 0;
+    CU_TRY(cudaDeviceSynchronize());
+    if (sk.ws) cudaFree(sk.ws);
+    if (sk.cnt) cudaFree(sk.cnt);
+    sk = SplitK();
+    CU_TRY(cudaMalloc(&sk.ws, (size_t)pairs * 256 * 256 * sizeof(float)));
+    CU_TRY(cudaMalloc(&sk.cnt, (size_t)pairs * 16 * sizeof(int)));
+    CU_TRY(cudaMemset(sk.cnt, 0, (size_t)pairs * 16 * sizeof(int)));
+    CU_TRY(cudaDeviceSynchronize());
+    sk.pairs = pairs;
+    return 0;
+}
 static int launch_gemm2(mb_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
-                        const GemmParams& p, int epi, int num_sms, cudaStream_t st) {
-    const int tiles = ((p.M + 255) / 256) * (p.N / 256);
+                        const GemmParams& p_in, int epi, int num_sms, cudaStream_t st) {
+    GemmParams p = p_in;
+    int tiles = ((p.M + 255) / 256) * (p.N / 256);
     int pairs = num_sms / 2;
-    if (tiles < pairs) pairs = tiles;
+    // small M: fewer tiles than half the CTA pairs -> cut K so that (almost) every pair gets a unit of >= 4 k-blocks
+    p.ksplit = 1;
+    if (tiles * 2 <= pairs) {
+        SplitK& sk = h ? h->splitk : g_splitk;
+        if (!h) MB_TRY(ensure_splitk(sk, pairs));
+        int ks = pairs / tiles;
+        const int num_k = p.K / 64;
+        if (ks > num_k / 4) ks = num_k / 4;
+        if (ks > 8) ks = 8;
+        if (ks > 1 && sk.ws && tiles * ks <= sk.pairs) {
+            p.ksplit = ks; p.splitk_ws = sk.ws; p.splitk_cnt = sk.cnt;
+            tiles *= ks;
+        }
+    }
+    static int l2_prefetch = -1;
+    if (l2_prefetch < 0) { const char* e = getenv("MASKBIT_B200_L2_PREFETCH"); l2_prefetch = e ? atoi(e) != 0 : 1; }
+    if (!l2_prefetch || tiles * 2 > pairs) p.prefetch = nullptr;   // idle pairs only pay when a good half of the GPU has no tile
+    if (tiles < pairs && !p.prefetch) pairs = tiles;
     const int grid = 2 * pairs, smem = gemm2_smem_bytes(epi);
     switch (epi) {
         case 0: CU_TRY(launch_k(gemm2_bf16_tcgen05_kernel<0>, grid, Gemm2Cfg::THREADS, smem, st, ta, tb, tc, tr, p)); break;
@@ -886,6 +947,10 @@ static int run_linear(mb_handle* h, int kind, const CUtensorMap& ta, const Linea
     p.M = M; p.N = L.N; p.K = L.K; p.bias = L.b; p.vec2 = L.v2; p.residual = residual; p.ldr = L.N;
     p.stats_in = stats_in; p.stats_out = stats_out; p.inv_d = 1.0f / (float)h->cfg.hidden_dim; p.eps = 1e-12f;
     p.out = out; p.ldo = ldo; p.seq_in = seq_in; p.seq_out = seq_out;
+    if (h && h->prefetch_next) {
+        p.prefetch = h->prefetch_next->w; p.prefetch_bytes = (unsigned long long)h->prefetch_next->N * h->prefetch_next->K * 2;
+        h->prefetch_next = nullptr;
+    }
     return launch_gemm(h, ta, L.tm, L.BN == 256 ? &L.tm_half : nullptr, tm_out, L.BN, p, epi, h->num_sms, st, tm_res);
 }
 
@@ -969,6 +1034,8 @@ static int forward_impl(mb_handle* h, const int64_t* tokens, int n_token_rows, c
     for (int l = 0; l < c.depth; ++l) {
         const Layer& L = h->layers[l];
         // attention block (bert.py:137-139): yB = out_proj(MHA(LN(yA))) + LN(yA)
+        // (h->prefetch_next: the Linear after the one being launched -- GemmParams::prefetch)
+        h->prefetch_next = &L.out;
         MB_TRY(run_linear(h, MB_PROF_GEMM_QKV, h->tm_yA, L.qkv, M, EPI_LNIN_BF16, nullptr, h->stA, nullptr, h->qkv, &h->tmo_qkv, 3 * D, st));
         MB_TRY(run_attention(h, h->tm_qkv_big, h->tm_qkv_row, h->tmo_att, h->qkv, h->att, n_seq, h->S, D, c.heads, h->num_sms, st));
         if (attn) {   // return_attn=True: this layer's head-averaged attention map, from the same qkv buffer (diagnostic side path)
@@ -977,12 +1044,16 @@ static int forward_impl(mb_handle* h, const int64_t* tokens, int n_token_rows, c
                                                                                   1.4426950408889634f / sqrtf((float)ATT_HD));
             CU_TRY(cudaGetLastError()); h->launches++;
         }
+        h->prefetch_next = &L.up;
         MB_TRY(run_linear(h, MB_PROF_GEMM_OUT, h->tm_att, L.out, M, EPI_RES_LN_BF16_STATS, h->yA, res_stA, h->stB, h->yB, &h->tmo_yB, D, st, 0, 0, &h->tmo_yA));
         // feed-forward block (bert.py:69-70): yA = W2 gelu(W1 LN1(yB) + b1) + b2 + LN1(yB)
+        h->prefetch_next = &L.down;
         MB_TRY(run_linear(h, MB_PROF_GEMM_UP, h->tm_yB, L.up, M, EPI_LNIN_GELU_BF16, nullptr, h->stB, nullptr, h->hmid, &h->tmo_hmid, c.mlp_dim, st));
+        h->prefetch_next = l + 1 < c.depth ? &h->layers[l + 1].qkv : &h->head;
         MB_TRY(run_linear(h, MB_PROF_GEMM_DOWN, h->tm_hmid, L.down, M, EPI_RES_LN_BF16_STATS, h->yB, res_stB, h->stA, h->yA, &h->tmo_yA, D, st, 0, 0, &h->tmo_yB));
     }
     // head (bert.py:500-503): LN(gelu(W LN2(yA) + b)) -> prediction layer, class-token row dropped
+    h->prefetch_next = c.depth > 0 ? &h->layers[0].qkv : nullptr;     // the next forward's first weights (the prediction layer's are small)
     MB_TRY(run_linear(h, MB_PROF_GEMM_HEAD, h->tm_yA, h->head, M, EPI_LNIN_GELU_BF16_STATS, nullptr, h->stA, h->stB, h->yB, &h->tmo_yB, D, st));
     MB_TRY(run_linear(h, MB_PROF_GEMM_HEAD, h->tm_yB, h->pred, M, EPI_LNIN_F32_SEQ, nullptr, h->stB, nullptr, logits, nullptr, h->pred.N, st, h->S, c.seq_len));
     if (h->pos_bias) {   // Bert: + bias[split][position][v] (bert.py:333)
@@ -1007,6 +1078,7 @@ extern "C" int mb_generator_forward_attn(mb_handle* h, const int64_t* tokens, in
 }
 
 // ------------------------------------------------------------------------------------------------ select
+static int test_num_sms();
 static int select_impl(mb_handle* h, const mb_select_args* a, cudaStream_t st) {
     SelectParams p;
     p.logits_c = a->logits_c; p.logits_u = a->logits_u; p.q = a->q; p.gumbel = a->gumbel;
@@ -1020,14 +1092,26 @@ static int select_impl(mb_handle* h, const mb_select_args* a, cudaStream_t st) {
     if (a->tokens_in == a->tokens_out) return fail(MB_ERR_INVALID, "select: tokens_in and tokens_out must be distinct buffers");
     const size_t smem = ((slots * 4 + 15) & ~15) + (size_t)slots * 8;
     ProfScope prof(h, MB_PROF_SELECT, st);
+    // small batches: a cluster of 8 CTAs per sample (SelectParams::csize); MASKBIT_B200_SELECT_CLUSTER=0 keeps one CTA per sample
+    static int use_cluster = -1;
+    if (use_cluster < 0) { const char* e = getenv("MASKBIT_B200_SELECT_CLUSTER"); use_cluster = e ? atoi(e) != 0 : 1; }
+    const int sms = h ? h->num_sms : test_num_sms();
+    p.csize = (use_cluster && a->B * 8 <= sms) ? 8 : 1;
+    const unsigned grid = (unsigned)(a->B * p.csize);
+#define MB_SELECT_LAUNCH(VPL)                                                                                              \
+    do {                                                                                                                   \
+        if (p.csize > 1) CU_TRY(launch_k_cluster(select_step_kernel<VPL>, grid, 512, smem, st, (unsigned)p.csize, p));     \
+        else CU_TRY(launch_k(select_step_kernel<VPL>, grid, 512, smem, st, p));                                            \
+    } while (0)
     switch (a->V) {
-        case 32: CU_TRY(launch_k(select_step_kernel<1>, a->B, 512, smem, st, p)); break;
-        case 64: CU_TRY(launch_k(select_step_kernel<2>, a->B, 512, smem, st, p)); break;
-        case 128: CU_TRY(launch_k(select_step_kernel<4>, a->B, 512, smem, st, p)); break;
-        case 256: CU_TRY(launch_k(select_step_kernel<8>, a->B, 512, smem, st, p)); break;
-        case 512: CU_TRY(launch_k(select_step_kernel<16>, a->B, 512, smem, st, p)); break;
+        case 32: MB_SELECT_LAUNCH(1); break;
+        case 64: MB_SELECT_LAUNCH(2); break;
+        case 128: MB_SELECT_LAUNCH(4); break;
+        case 256: MB_SELECT_LAUNCH(8); break;
+        case 512: MB_SELECT_LAUNCH(16); break;
         default: return fail(MB_ERR_INVALID, "select: vocabulary %d unsupported", a->V);
     }
+#undef MB_SELECT_LAUNCH
     CU_TRY(cudaGetLastError());
     if (h) h->launches++;
     return 0;

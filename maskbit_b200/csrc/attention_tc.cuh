@@ -89,7 +89,6 @@ __device__ __forceinline__ void tmem_st_32x32_x16(uint32_t taddr, const uint32_t
         "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
 }
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // MN-major operand tile stored as rows (K index) of 128 bytes (64 contiguous MN elements) with the 128-byte swizzle;
 // 8 K-rows per 1024 B atom (stride-dim byte offset), one 64-element MN block (leading-dim offset unused).
@@ -183,7 +182,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
     uint32_t* retry_mask = reinterpret_cast<uint32_t*>(bars + 32);                               // [ATC_RETRY_CAP / 32]
     uint16_t* retry_list = reinterpret_cast<uint16_t*>(retry_mask + ATC_RETRY_CAP / 32);         // [ATC_RETRY_CAP]
+#if ATC_FASTMAX
     int* retry_count = reinterpret_cast<int*>(retry_list + ATC_RETRY_CAP);
+#endif
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_big); tma_prefetch_desc(&tm_row); }
@@ -215,7 +216,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
   for (int round = 0; round < (ATC_FASTMAX ? 2 : 1); ++round) {
     const int k0 = round ? n_local : 0, k1 = round ? n_local + n_retry : n_local;
     const bool exact = round != 0 || !fast_round;
-    (void)exact; (void)retry_count;
+    (void)exact;
 
     if (warp == 0) {
         if (elect_one()) {  // -------------------------------------------------------------- TMA producer

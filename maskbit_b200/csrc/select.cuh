@@ -8,6 +8,7 @@
 // the polynomial kernels below, sums as lane-strided sequential adds followed by a 5-level xor butterfly.  The plain-C
 // oracle (oracle/select_oracle.c) states the same contract independently; outputs agree bit-for-bit.
 #pragma once
+#include "ptx.cuh"
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -101,6 +102,9 @@ struct SelectParams {
     int64_t mask_token;
     uint64_t seed;              // Philox key (production mode)
     uint32_t step;
+    int csize;                  // CTAs per sample: 1, or a thread-block cluster of 8 for small batches (one CTA per sample leaves a
+                                // batch-1 step on a single SM for ~100 us): the slots are dealt over the cluster's warps, confidences
+                                // and predictions land in rank 0's shared memory (DSMEM stores), rank 0 ranks and writes out
 };
 
 // VPL = V / 32 values per lane.  blockDim = 512; dynamic smem: slots * (4 + 8) bytes.
@@ -112,7 +116,9 @@ __global__ void __launch_bounds__(512) select_step_kernel(SelectParams p) {
     int64_t* pred_s = reinterpret_cast<int64_t*>(sel_smem + ((slots * 4 + 15) & ~15));
     __shared__ int s_count;
     __shared__ float s_thr;
-    const int b = blockIdx.x;
+    const int cs = p.csize;
+    const int b = blockIdx.x / cs;
+    const uint32_t crank = cs > 1 ? cluster_ctarank() : 0u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int V = VPL * 32;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");    // programmatic dependent launch (ptx.cuh): the logits come from
@@ -126,7 +132,7 @@ __global__ void __launch_bounds__(512) select_step_kernel(SelectParams p) {
     cnt = __reduce_add_sync(0xffffffffu, cnt);
     if (lane == 0 && cnt) atomicAdd(&s_count, cnt);
 
-    for (int s = warp; s < slots; s += nwarps) {
+    for (int s = (int)crank * nwarps + warp; s < slots; s += nwarps * cs) {
         const int pos = s / p.m, g = s - pos * p.m;
         const size_t off = (((size_t)b * p.seq_stride + pos) * p.m + g) * V;
         const int64_t tin = p.tokens_in[(size_t)b * slots + s];
@@ -211,9 +217,19 @@ __global__ void __launch_bounds__(512) select_step_kernel(SelectParams p) {
                 const float nz = __fmul_rn(__fmul_rn(gz, p.randomize_temperature), p.one_minus_progress);
                 c = __fadd_rn(sel_logf(ptok), nz);
             }
-            conf[s] = c;
-            pred_s[s] = masked ? (int64_t)besti : tin;
+            const int64_t pv = masked ? (int64_t)besti : tin;
+            if (cs > 1) {   // into rank 0's copy of conf / pred_s
+                asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(mapa_u32(smem_u32(conf + s), 0)), "f"(c) : "memory");
+                asm volatile("st.shared::cluster.b64 [%0], %1;" ::"r"(mapa_u32(smem_u32(pred_s + s), 0)), "l"(pv) : "memory");
+            } else {
+                conf[s] = c;
+                pred_s[s] = pv;
+            }
         }
+    }
+    if (cs > 1) {
+        cluster_sync_all();          // release / acquire at cluster scope: every rank's DSMEM stores are visible to rank 0
+        if (crank != 0) return;
     }
     __syncthreads();
     // k (torch.clamp semantics: lower bound first, then the upper bound wins), python index k-1 may wrap to the last
