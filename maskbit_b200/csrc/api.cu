@@ -900,7 +900,7 @@ static int launch_gemm2(mb_handle* h, const CUtensorMap& ta, const CUtensorMap& 
     }
     static int l2_prefetch = -1;
     if (l2_prefetch < 0) { const char* e = getenv("MASKBIT_B200_L2_PREFETCH"); l2_prefetch = e ? atoi(e) != 0 : 1; }
-    if (!l2_prefetch || tiles * 2 > pairs) p.prefetch = nullptr;   // idle pairs only pay when a good half of the GPU has no tile
+    if (!l2_prefetch || tiles >= pairs) p.prefetch = nullptr;      // no idle pair, nobody to prefetch
     if (tiles < pairs && !p.prefetch) pairs = tiles;
     const int grid = 2 * pairs, smem = gemm2_smem_bytes(epi);
     switch (epi) {
@@ -1364,7 +1364,7 @@ static int decode_impl(mb_handle* h, const int64_t* tokens, int B, float* images
             }
         }
         MB_TRY(run_gn(h, X, h->norm_out, nb, R, st));
-        dim3 grid((R + CO_T - 1) / CO_T, (R + CO_T - 1) / CO_T, nb);
+        dim3 grid((R + CO_TX - 1) / CO_TX, (R + CO_TY - 1) / CO_TY, nb);
         { ProfScope prof(h, MB_PROF_DEC_IO, st);
         conv_out_kernel<<<grid, 256, 0, st>>>(X, h->gn_scale, h->gn_shift, h->cout_w, h->cout_b, images + (size_t)b0 * 3 * R * R, R, R, h->dec_cl); }
         CU_TRY(cudaGetLastError()); h->launches++;

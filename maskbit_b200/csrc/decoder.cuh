@@ -133,21 +133,31 @@ __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x));
 
 // ------------------------------------------------------------------------------------------------ conv_out
 // in fp32 NHWC [B,H,W,C] -> GroupNorm-apply + SiLU -> 3x3 conv to 3 channels (+bias) -> fp32 NCHW [B,3,H,W].
-// w fp32 [9][C][4] (4th lane zero), 16x16 output tile per CTA, channels streamed through smem 16 at a time.
-constexpr int CO_T = 16, CO_CC = 16;
+// w fp32 [9][C][4] (4th lane zero).  One CTA = 16 rows x 64 columns of outputs, one thread = 4 consecutive pixels of a row
+// (12 accumulators); channels stream through shared memory 8 at a time as PLANES [c][row][x] (x contiguous), so a thread reads
+// its 6 inputs of a tap row with one 128-bit + one 64-bit load and every weight float4 is reused for 4 pixels:
+// 15 shared-memory loads per 108 FMAs (one pixel per thread with [pixel][c] tiles was 2 loads per 3 FMAs and LDS-bound,
+// 1.36 ms per 32 images against 0.16 ms of HBM time: profiles/r02_launches_B256_T1.txt).
+constexpr int CO_TY = 16, CO_TX = 64, CO_CC = 8;
+constexpr int CO_PITCH = CO_TX + 4;                        // 66 columns with the halo, padded to a multiple of 4 floats
+constexpr int CO_PLANE = (CO_TY + 2) * CO_PITCH + 4;       // +4: planes 4 apart land 16 banks apart (conflict-free fill stores)
 __global__ void __launch_bounds__(256)
 conv_out_kernel(const float* __restrict__ in, const float* __restrict__ gn_scale, const float* __restrict__ gn_shift,
                 const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out, int H, int W, int C) {
-    __shared__ float tile[(CO_T + 2) * (CO_T + 2)][CO_CC + 1];
+    __shared__ __align__(16) float tile[CO_CC * CO_PLANE];
     __shared__ float4 wsm[9][CO_CC];
-    const int n = blockIdx.z, ty0 = blockIdx.y * CO_T, tx0 = blockIdx.x * CO_T;
+    const int n = blockIdx.z, ty0 = blockIdx.y * CO_TY, tx0 = blockIdx.x * CO_TX;
     const int lx = threadIdx.x & 15, ly = threadIdx.x >> 4;
-    float a0 = bias[0], a1 = bias[1], a2 = bias[2];
+    float acc[4][3];
+#pragma unroll
+    for (int px = 0; px < 4; ++px) { acc[px][0] = bias[0]; acc[px][1] = bias[1]; acc[px][2] = bias[2]; }
     for (int c0 = 0; c0 < C; c0 += CO_CC) {
         __syncthreads();
-        for (int i = threadIdx.x; i < (CO_T + 2) * (CO_T + 2) * (CO_CC / 4); i += 256) {
-            const int c4 = i % (CO_CC / 4), pix = i / (CO_CC / 4);
-            const int yy = ty0 + pix / (CO_T + 2) - 1, xx = tx0 + pix % (CO_T + 2) - 1;
+        // fill: lanes (pixel, half) -> the pixel's 32-byte sector of 8 channels is read by two adjacent lanes
+        for (int i = threadIdx.x; i < (CO_TY + 2) * (CO_TX + 2) * 2; i += 256) {
+            const int c4 = i & 1, pix = i >> 1;
+            const int row = pix / (CO_TX + 2), sx = pix - row * (CO_TX + 2);
+            const int yy = ty0 + row - 1, xx = tx0 + sx - 1;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
                 v = __ldg(reinterpret_cast<const float4*>(in + (((size_t)n * H + yy) * W + xx) * C + c0 + c4 * 4));
@@ -156,7 +166,8 @@ conv_out_kernel(const float* __restrict__ in, const float* __restrict__ gn_scale
                 v.x = silu(fmaf(v.x, a.x, b.x)); v.y = silu(fmaf(v.y, a.y, b.y));
                 v.z = silu(fmaf(v.z, a.z, b.z)); v.w = silu(fmaf(v.w, a.w, b.w));
             }
-            tile[pix][c4 * 4 + 0] = v.x; tile[pix][c4 * 4 + 1] = v.y; tile[pix][c4 * 4 + 2] = v.z; tile[pix][c4 * 4 + 3] = v.w;
+            float* dst = tile + (c4 * 4) * CO_PLANE + row * CO_PITCH + sx;
+            dst[0] = v.x; dst[CO_PLANE] = v.y; dst[2 * CO_PLANE] = v.z; dst[3 * CO_PLANE] = v.w;
         }
         for (int i = threadIdx.x; i < 9 * CO_CC; i += 256) {
             const int tap = i / CO_CC, c = i % CO_CC;
@@ -164,21 +175,37 @@ conv_out_kernel(const float* __restrict__ in, const float* __restrict__ gn_scale
         }
         __syncthreads();
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-            const float* tp = tile[(ly + tap / 3) * (CO_T + 2) + lx + tap % 3];
+        for (int c = 0; c < CO_CC; ++c) {
 #pragma unroll
-            for (int c = 0; c < CO_CC; ++c) {
-                const float v = tp[c];
-                const float4 ww = wsm[tap][c];
-                a0 = fmaf(v, ww.x, a0); a1 = fmaf(v, ww.y, a1); a2 = fmaf(v, ww.z, a2);
+            for (int dy = 0; dy < 3; ++dy) {
+                const float* rp = tile + c * CO_PLANE + (ly + dy) * CO_PITCH + 4 * lx;
+                const float4 v0 = *reinterpret_cast<const float4*>(rp);
+                const float2 v1 = *reinterpret_cast<const float2*>(rp + 4);
+                const float v[6] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y};
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const float4 ww = wsm[dy * 3 + dx][c];
+#pragma unroll
+                    for (int px = 0; px < 4; ++px) {
+                        acc[px][0] = fmaf(v[px + dx], ww.x, acc[px][0]);
+                        acc[px][1] = fmaf(v[px + dx], ww.y, acc[px][1]);
+                        acc[px][2] = fmaf(v[px + dx], ww.z, acc[px][2]);
+                    }
+                }
             }
         }
     }
-    const int y = ty0 + ly, x = tx0 + lx;
+    const int y = ty0 + ly, x = tx0 + 4 * lx;
     if (y < H && x < W) {
         const size_t hw = (size_t)H * W;
         float* o = out + (size_t)n * 3 * hw + (size_t)y * W + x;
-        o[0] = a0; o[hw] = a1; o[2 * hw] = a2;
+        if (x + 3 < W && (W & 3) == 0) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch)
+                *reinterpret_cast<float4*>(o + ch * hw) = make_float4(acc[0][ch], acc[1][ch], acc[2][ch], acc[3][ch]);
+        } else {
+            for (int px = 0; px < 4 && x + px < W; ++px) { o[px] = acc[px][0]; o[hw + px] = acc[px][1]; o[2 * hw + px] = acc[px][2]; }
+        }
     }
 }
 

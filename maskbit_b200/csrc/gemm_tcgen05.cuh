@@ -60,6 +60,9 @@
 #else
 #define GEMM_EV(role, ev, it, val) do {} while (0)
 #endif
+#ifndef GEMM_EPI7_PIPE
+#define GEMM_EPI7_PIPE 1         // residual epilogue (CTA-pair kernel): TMEM loads one chunk ahead of the math
+#endif
 #ifndef GEMM_RES_PREFETCH
 #define GEMM_RES_PREFETCH 1      // residual epilogue: load the thread's residual-row slab before the accumulator wait
 #endif
@@ -295,11 +298,8 @@ __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, u
     const long long out_row = er.out_row;
     const float rs = er.rs, nmr = er.nmr;
     float st_sum = 0.f, st_sq = 0.f, st_sum1 = 0.f, st_sq1 = 0.f;   // even / odd column partial sums (packed pairs)
-    auto chunk = [&](const int c) {
+    auto chunk_v = [&](const int c, const uint32_t (&v)[32]) {
         const int col0 = half * COLS_PER_WARP + c;
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + col0, v);
-        tmem_ld_wait();
         const int n0 = n_blk * BN + col0;
         float f[32];
 #pragma unroll
@@ -401,7 +401,29 @@ __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, u
             for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
         }
     };
-    if constexpr (kPre) {   // prefetched slab: indices must be compile-time constants to stay in registers
+    auto chunk = [&](const int c) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + half * COLS_PER_WARP + c, v);
+        tmem_ld_wait();
+        chunk_v(c, v);
+    };
+    if constexpr (kResS && GEMM_EPI7_PIPE && COLS_PER_WARP % 64 == 0) {
+        // Residual epilogue of the CTA-pair kernel (K = 1024 out-projection: 2 k clk of MMAs per tile, the epilogue is the longer
+        // side): the accumulator chunk c+1 is on its way out of TMEM while chunk c is processed, instead of one exposed
+        // tcgen05.ld round trip per chunk.
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(taddr + half * COLS_PER_WARP, va);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < COLS_PER_WARP; c += 64) {
+            tmem_ld_32x32(taddr + half * COLS_PER_WARP + c + 32, vb);
+            chunk_v(c, va);
+            tmem_ld_wait();
+            if (c + 64 < COLS_PER_WARP) tmem_ld_32x32(taddr + half * COLS_PER_WARP + c + 64, va);
+            chunk_v(c + 32, vb);
+            if (c + 64 < COLS_PER_WARP) tmem_ld_wait();
+        }
+    } else if constexpr (kPre) {   // prefetched slab: indices must be compile-time constants to stay in registers
 #pragma unroll
         for (int c = 0; c < COLS_PER_WARP; c += 32) chunk(c);
     } else {
