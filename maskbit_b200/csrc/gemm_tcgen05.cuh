@@ -60,9 +60,6 @@
 #else
 #define GEMM_EV(role, ev, it, val) do {} while (0)
 #endif
-#ifndef GEMM_EPI7_PIPE
-#define GEMM_EPI7_PIPE 1         // residual epilogue (CTA-pair kernel): TMEM loads one chunk ahead of the math
-#endif
 #ifndef GEMM_RES_PREFETCH
 #define GEMM_RES_PREFETCH 1      // residual epilogue: load the thread's residual-row slab before the accumulator wait
 #endif
@@ -407,23 +404,10 @@ __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, u
         tmem_ld_wait();
         chunk_v(c, v);
     };
-    if constexpr (kResS && GEMM_EPI7_PIPE && COLS_PER_WARP % 64 == 0) {
-        // Residual epilogue of the CTA-pair kernel (K = 1024 out-projection: 2 k clk of MMAs per tile, the epilogue is the longer
-        // side): the accumulator chunk c+1 is on its way out of TMEM while chunk c is processed, instead of one exposed
-        // tcgen05.ld round trip per chunk.
-        uint32_t va[32], vb[32];
-        tmem_ld_32x32(taddr + half * COLS_PER_WARP, va);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < COLS_PER_WARP; c += 64) {
-            tmem_ld_32x32(taddr + half * COLS_PER_WARP + c + 32, vb);
-            chunk_v(c, va);
-            tmem_ld_wait();
-            if (c + 64 < COLS_PER_WARP) tmem_ld_32x32(taddr + half * COLS_PER_WARP + c + 64, va);
-            chunk_v(c + 32, vb);
-            if (c + 64 < COLS_PER_WARP) tmem_ld_wait();
-        }
-    } else if constexpr (kPre) {   // prefetched slab: indices must be compile-time constants to stay in registers
+    // (Loading the accumulator chunk c+1 out of TMEM while chunk c is processed was tried for the residual epilogue of the K = 1024
+    //  out-projection and changed nothing, isolated or sustained: profiles/r02_epi7_pipe_neutral.txt.  That GEMM runs at 81 % tensor-pipe
+    //  time next to 50-60 % of the HBM rate -- A, the residual stream and the output are each as large as the weights are small.)
+    if constexpr (kPre) {   // prefetched slab: indices must be compile-time constants to stay in registers
 #pragma unroll
         for (int c = 0; c < COLS_PER_WARP; c += 32) chunk(c);
     } else {
