@@ -288,10 +288,8 @@ struct GNW { float* g = nullptr; float* b = nullptr; int C = 0; };
 struct ResBlockW { GNW n1, n2; ConvW c1, c2, nin; bool has_nin = false; };
 struct StageW { std::vector<ResBlockW> blocks; bool has_up = false; ConvW up; };
 
-struct SplitK { float* ws = nullptr; int* cnt = nullptr; int pairs = 0; };
 struct mb_handle {
     mb_config cfg;
-    SplitK splitk;
     const struct Linear* prefetch_next = nullptr;   // the Linear that runs after the next run_linear (its weights are prefetched into L2)
     int device = 0, num_sms = 148;
     int64_t launches = 0;
@@ -458,8 +456,6 @@ extern "C" void mb_destroy(mb_handle* h) {
     for (int m = 0; m < 2; ++m) for (auto& kv : h->staged[m]) cudaFree(kv.second.ptr);
     for (void* p : h->allocs) cudaFree(p);
     free_ws(h); free_sample_ws(h); free_dec_ws(h);
-    if (h->splitk.ws) cudaFree(h->splitk.ws);
-    if (h->splitk.cnt) cudaFree(h->splitk.cnt);
     for (int i = 0; i < 2; ++i) { if (h->dstream[i]) cudaStreamDestroy(h->dstream[i]); if (h->dev_join[i]) cudaEventDestroy(h->dev_join[i]); }
     if (h->dev_fork) cudaEventDestroy(h->dev_fork);
     if (h->gstream) cudaStreamDestroy(h->gstream);
@@ -821,13 +817,11 @@ static int init_kernel_attrs() {
     return 0;
 }
 
-static int ensure_splitk(SplitK& sk, int pairs);
 extern "C" int mb_finalize(mb_handle* h, int model) {
     if (!h || model < 0 || model > 1) return fail(MB_ERR_INVALID, "mb_finalize: bad argument");
     if (h->finalized[model]) return fail(MB_ERR_STATE, "model %d already finalized", model);
     MB_TRY(init_kernel_attrs());
     MB_TRY(model == MB_GENERATOR ? finalize_generator(h) : finalize_tokenizer(h));
-    if (model == MB_GENERATOR) MB_TRY(ensure_splitk(h->splitk, h->num_sms / 2));
     CU_TRY(cudaDeviceSynchronize());
     h->finalized[model] = true;
     return 0;
@@ -857,47 +851,14 @@ static int launch_gemm_bn(mb_handle* h, const CUtensorMap& ta, const CUtensorMap
     if (h) h->launches++;
     return 0;
 }
-// Split-K scratch of the CTA-pair kernel (GemmParams::ksplit), sized for one unit per CTA pair: one per handle (allocated when the
-// generator is finalized, so never inside a stream capture) and a process-wide one for the handle-less test hooks.
-// GEMMs sharing a scratch must not overlap in time (a handle's forwards are stream-ordered).
-// OFF by default (MASKBIT_B200_SPLITK=1 turns it on): correct (kernel tests green with it on) but slower than the un-split schedule at
-// batch 1 -- down-projection 30 -> 70 us, out-projection 17 -> 52 us (profiles/r02_splitk_rejected.txt): the fix-up is a chain of
-// L2 round trips per warp.  What helps that corner is the L2 prefetch by idle pairs (GemmParams::prefetch).
-static SplitK g_splitk;
-static int g_splitk_on = -1;
-static int ensure_splitk(SplitK& sk, int pairs) {
-    if (g_splitk_on < 0) { const char* e = getenv("MASKBIT_B200_SPLITK"); g_splitk_on = e ? atoi(e) != 0 : 0; }
-    if (!g_splitk_on || pairs <= sk.pairs) return 0;
-    CU_TRY(cudaDeviceSynchronize());
-    if (sk.ws) cudaFree(sk.ws);
-    if (sk.cnt) cudaFree(sk.cnt);
-    sk = SplitK();
-    CU_TRY(cudaMalloc(&sk.ws, (size_t)pairs * 256 * 256 * sizeof(float)));
-    CU_TRY(cudaMalloc(&sk.cnt, (size_t)pairs * 16 * sizeof(int)));
-    CU_TRY(cudaMemset(sk.cnt, 0, (size_t)pairs * 16 * sizeof(int)));
-    CU_TRY(cudaDeviceSynchronize());
-    sk.pairs = pairs;
-    return 0;
-}
 static int launch_gemm2(mb_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
                         const GemmParams& p_in, int epi, int num_sms, cudaStream_t st) {
     GemmParams p = p_in;
-    int tiles = ((p.M + 255) / 256) * (p.N / 256);
+    const int tiles = ((p.M + 255) / 256) * (p.N / 256);
     int pairs = num_sms / 2;
-    // small M: fewer tiles than half the CTA pairs -> cut K so that (almost) every pair gets a unit of >= 4 k-blocks
-    p.ksplit = 1;
-    if (tiles * 2 <= pairs) {
-        SplitK& sk = h ? h->splitk : g_splitk;
-        if (!h) MB_TRY(ensure_splitk(sk, pairs));
-        int ks = pairs / tiles;
-        const int num_k = p.K / 64;
-        if (ks > num_k / 4) ks = num_k / 4;
-        if (ks > 8) ks = 8;
-        if (ks > 1 && sk.ws && tiles * ks <= sk.pairs) {
-            p.ksplit = ks; p.splitk_ws = sk.ws; p.splitk_cnt = sk.cnt;
-            tiles *= ks;
-        }
-    }
+    // (A split-K schedule for small M -- K slices of a tile on different pairs, partial accumulators through L2, the last-arriving
+    //  warp summing in slice order -- was built and measured: correct, but the fix-up's chain of L2 round trips made the batch-1
+    //  down-projection 30 -> 70 us; removed again, numbers in profiles/r02_splitk_rejected.txt.)
     static int l2_prefetch = -1;
     if (l2_prefetch < 0) { const char* e = getenv("MASKBIT_B200_L2_PREFETCH"); l2_prefetch = e ? atoi(e) != 0 : 1; }
     if (!l2_prefetch || tiles >= pairs) p.prefetch = nullptr;      // no idle pair, nobody to prefetch

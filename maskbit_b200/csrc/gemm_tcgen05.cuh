@@ -94,11 +94,6 @@ struct GemmParams {
     int ldo;
     int seq_in, seq_out;             // *_SEQ: rows per sequence in A / kept rows per sequence in out
     long long* trace = nullptr;      // GEMM_TRACE builds: [roles 4][events 4][tiles 32] clock64 stamps, else unused
-    // CTA-pair kernel, small M (fewer 256 x 256 tiles than CTA pairs): every tile's K loop is cut into `ksplit` slices that run
-    // on different pairs, so that all SMs pull the weights (a pair streams its k-blocks at ~120 GB/s per SM; 12 pairs on an
-    // 8 MB weight matrix took 17 us).  Each epilogue warp parks its fp32 partial accumulators in `splitk_ws`; the warp that
-    // arrives last on the region's counter sums all slices IN SLICE ORDER (run-to-run identical), writes the sum back to TMEM
-    // and runs the normal epilogue.
     // CTA-pair kernel, small M: the launch still fills the GPU and the pairs WITHOUT a tile pull the NEXT GEMM's weight matrix into
     // L2 (cp.async.bulk.prefetch.L2), before griddepcontrol.wait -- weights do not depend on the predecessor.  At batch 1 a forward
     // is a weight stream (610 MB per forward, no reuse), and a 12-tile GEMM reading its 8 MB from HBM through 24 SMs is bound by
@@ -106,9 +101,6 @@ struct GemmParams {
     // GEMM's own loads hit L2.
     const void* prefetch = nullptr;
     unsigned long long prefetch_bytes = 0;
-    int ksplit = 1;
-    float* splitk_ws = nullptr;      // [tiles][ksplit][2 CTAs][8 warps][4 chunks][32 lanes][32] fp32
-    int* splitk_cnt = nullptr;       // [tiles][2][8] arrival counters, zero between launches (the last arriver resets its own)
 };
 
 template <int BN>
@@ -602,8 +594,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
     const int num_m = (p.M + C::BM - 1) / C::BM, num_n = p.N / BN;
-    const int num_k = p.K / BK, ksplit = p.ksplit;
-    const int num_tiles = num_m * num_n * ksplit;    // work units: (output tile, K slice), slices of a tile consecutive
+    const int num_tiles = num_m * num_n, num_k = p.K / BK;
 
     if (warp == W_PROD && lane == 0) {
         tma_prefetch_desc(&tm_a);
@@ -641,21 +632,19 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
         if (elect_one()) {  // ---------------- TMA producer (each CTA: its 128 A rows, its 128 of the 256 B rows)
             int stage = 0; uint32_t phase = 0;
             uint32_t it = 0;
-            for (int unit = pair; unit < num_tiles; unit += num_pairs, ++it) {
-                const int tile = unit / ksplit, ks = unit - tile * ksplit;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
                 const int m_blk = tile / num_n, n_blk = tile % num_n;
-                const int kb0 = ks * num_k / ksplit, kb1 = (ks + 1) * num_k / ksplit;
 #if GEMM_TRACE
                 long long empty_wait = 0;
 #endif
-                for (int kb = kb0; kb < kb1; ++kb) {
+                for (int kb = 0; kb < num_k; ++kb) {
 #if GEMM_TRACE
                     const long long t0 = clock64();
 #endif
                     mbar_wait(&empty[stage], phase ^ 1);
 #if GEMM_TRACE
                     empty_wait += clock64() - t0;
-                    if (kb == kb1 - 1) { GEMM_EV(2, 0, it, empty_wait); GEMM_EV(2, 1, it, clock64()); }
+                    if (kb == num_k - 1) { GEMM_EV(2, 0, it, empty_wait); GEMM_EV(2, 1, it, clock64()); }
 #endif
                     if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (C::A_BYTES + C::B_BYTES));
                     const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
@@ -669,9 +658,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
         if (leader && elect_one()) {  // ---------------- MMA issuer (leader CTA only)
             constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, 256, BN);
             int stage = 0; uint32_t phase = 0; uint32_t it = 0;
-            for (int unit = pair; unit < num_tiles; unit += num_pairs, ++it) {
-                const int ks = unit % ksplit;
-                const int kb0 = ks * num_k / ksplit, kb1 = (ks + 1) * num_k / ksplit;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
                 const uint32_t as = it & 1, aphase = (it >> 1) & 1;
                 GEMM_EV(0, 0, it, clock64());
                 mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -681,7 +668,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
 #if GEMM_TRACE
                 long long full_wait = 0;
 #endif
-                for (int kb = kb0; kb < kb1; ++kb) {
+                for (int kb = 0; kb < num_k; ++kb) {
 #if GEMM_TRACE
                     const long long t0 = clock64();
 #endif
@@ -694,7 +681,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
                     const uint64_t b_desc = make_sdesc_k128(smem_u32(smem_b + stage * C::B_BYTES));
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
-                        if (!GEMM_TIMING_NO_MMA) umma_f16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, ((kb - kb0) | k) != 0);
+                        if (!GEMM_TIMING_NO_MMA) umma_f16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
                     umma_commit_2sm(&empty[stage], 3);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -713,17 +700,16 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
         const float* vsrc = e < BN / 2 ? p.bias : p.vec2;
         const int vcol = 2 * (e & (BN / 2 - 1));
         float2 vreg = make_float2(0.f, 0.f);
-        if (pair < num_tiles && vsrc) vreg = __ldg(reinterpret_cast<const float2*>(vsrc + ((pair / ksplit) % num_n) * BN + vcol));
+        if (pair < num_tiles && vsrc) vreg = __ldg(reinterpret_cast<const float2*>(vsrc + (pair % num_n) * BN + vcol));
         uint32_t it = 0;
-        for (int unit = pair; unit < num_tiles; unit += num_pairs, ++it) {
-            const int tile = unit / ksplit, ks = unit - tile * ksplit;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
             const int m_blk = tile / num_n, n_blk = tile % num_n;
             const uint32_t as = it & 1, aphase = (it >> 1) & 1;
             named_bar_sync(1, C::EPI_WARPS * 32);                       // every warp has finished reading the previous tile's vectors
             reinterpret_cast<float2*>(smem_vec)[e] = vreg;
             named_bar_sync(2, C::EPI_WARPS * 32);
-            if (unit + num_pairs < num_tiles && vsrc)
-                vreg = __ldg(reinterpret_cast<const float2*>(vsrc + (((unit + num_pairs) / ksplit) % num_n) * BN + vcol));
+            if (tile + num_pairs < num_tiles && vsrc)
+                vreg = __ldg(reinterpret_cast<const float2*>(vsrc + ((tile + num_pairs) % num_n) * BN + vcol));
             const int row0 = m_blk * C::BM + (int)rank * 128 + quarter * 32;
             const EpiRow er = epi_prepare<EPI>(p, row0 + lane);
             constexpr int CPW = BN / (C::EPI_WARPS / 4);
@@ -746,59 +732,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
             tc_fence_after();
             if (ew == 0 && lane == 0) GEMM_EV(1, 1, it, clock64());
             if constexpr (kResTma) mbar_wait(&res_full[ew], it & 1);
-            bool last_slice = true;
-            if (ksplit > 1) {
-                // this warp's region of the tile: 32 rows (TMEM lanes) x CPW columns, as CPW / 32 chunks of [32 lanes][32 floats]
-                const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + half * CPW;
-                const size_t region = ((size_t)rank * C::EPI_WARPS + ew) * (CPW * 32);
-                const size_t slice_stride = (size_t)2 * C::EPI_WARPS * CPW * 32;
-                float* ws_tile = p.splitk_ws + (size_t)tile * ksplit * slice_stride + region + lane * 32;
-                {
-                    float4* dst = reinterpret_cast<float4*>(ws_tile + ks * slice_stride);
-#pragma unroll 1
-                    for (int c = 0; c < CPW / 32; ++c) {
-                        uint32_t v[32];
-                        tmem_ld_32x32(tacc + c * 32, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            __stcg(dst + c * 256 + j, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
-                    }
-                }
-                __threadfence();
-                __syncwarp();
-                int* cnt = p.splitk_cnt + ((size_t)tile * 2 + rank) * C::EPI_WARPS + ew;
-                int old = 0;
-                if (lane == 0) old = atomicAdd(cnt, 1);
-                old = __shfl_sync(0xffffffffu, old, 0);
-                last_slice = old == ksplit - 1;
-                if (last_slice) {
-                    __threadfence();
-                    if (lane == 0) *cnt = 0;
-#pragma unroll 1
-                    for (int c = 0; c < CPW / 32; ++c) {
-                        float acc[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-#pragma unroll 1
-                        for (int s = 0; s < ksplit; ++s) {
-                            const float4* src = reinterpret_cast<const float4*>(ws_tile + s * slice_stride) + c * 256;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 q = __ldcg(src + j);
-                                acc[4 * j] += q.x; acc[4 * j + 1] += q.y; acc[4 * j + 2] += q.z; acc[4 * j + 3] += q.w;
-                            }
-                        }
-                        uint32_t v[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(acc[j]);
-                        tmem_st_32x32(tacc + c * 32, v);
-                    }
-                    tmem_st_wait();
-                }
-            }
-            if (!GEMM_TIMING_NO_EPI && last_slice)
+            if (!GEMM_TIMING_NO_EPI)
             epi_run<BN, EPI, kTma, C::EPI_WARPS / 4, kPre, true, kResTma>(p, er, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN,
                                                                           n_blk, half, EpiStage{stg_w, &tm_c, row0}, slab.v, smem_vec);
             tc_fence_before();
