@@ -886,6 +886,17 @@ static int launch_gemm2(mb_handle* h, const CUtensorMap& ta, const CUtensorMap& 
 // tr: the residual tensor's map (box 64 x 32, like tc) for the residual epilogue of the CTA-pair kernel
 static int launch_gemm(mb_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tb_half, const CUtensorMap* tc,
                        int BN, const GemmParams& p, int epi, int num_sms, cudaStream_t st, const CUtensorMap* tr = nullptr) {
+    // Small M (batch 1-4): a launch is ONE tile per CTA and its time is the tile's serial K loop (512 clk per k-block for a
+    // 256 x 256 pair tile: 17 us for the K = 4096 down-projection, tools/gemm_small_trace.py).  When 128 x 128 tiles still fit in one
+    // wave, the 1-CTA kernel with BN = 128 halves that chain (MASKBIT_B200_SMALL_M=0: off).
+    static int small_m = -1;
+    if (small_m < 0) { const char* e = getenv("MASKBIT_B200_SMALL_M"); small_m = e ? atoi(e) != 0 : 1; }
+    if (small_m && g_use_2cta && tb_half && BN == 256 && p.K % 64 == 0 && p.N % 128 == 0 &&
+        ((p.M + 127) / 128) * (p.N / 128) <= num_sms) {
+        if ((epi == EPI_RES_LN_BF16_STATS || epi == EPI_LNIN_GELU_BF16_STATS) && p.N != 128 * LN_PARTIALS)
+            return fail(MB_ERR_INVALID, "row-statistics epilogue needs N=%d (got N=%d)", 128 * LN_PARTIALS, p.N);
+        return launch_gemm_bn<128>(h, ta, *tb_half, p, epi, num_sms, st);
+    }
     if (g_use_2cta && tb_half && (tc || !gemm2_tma_store(epi)) && (tr || !gemm2_res_tma(epi)) && BN == 256 && p.K % 64 == 0 &&
         p.N % 256 == 0 && num_sms >= 2) {
         if ((epi == EPI_RES_LN_BF16_STATS || epi == EPI_LNIN_GELU_BF16_STATS) && p.N != 128 * LN_PARTIALS)
@@ -893,8 +904,8 @@ static int launch_gemm(mb_handle* h, const CUtensorMap& ta, const CUtensorMap& t
         return launch_gemm2(h, ta, *tb_half, tc ? *tc : ta, tr ? *tr : ta, p, epi, num_sms, st);
     }
     if (p.K % 64 || p.N % BN) return fail(MB_ERR_INVALID, "gemm shape M=%d N=%d K=%d BN=%d", p.M, p.N, p.K, BN);
-    if ((epi == EPI_RES_LN_BF16_STATS || epi == EPI_LNIN_GELU_BF16_STATS) && (BN != 256 || p.N != 128 * LN_PARTIALS))
-        return fail(MB_ERR_INVALID, "row-statistics epilogue needs N=%d, BN=256 (got N=%d BN=%d)", 128 * LN_PARTIALS, p.N, BN);
+    if ((epi == EPI_RES_LN_BF16_STATS || epi == EPI_LNIN_GELU_BF16_STATS) && ((BN != 256 && BN != 128) || p.N != 128 * LN_PARTIALS))
+        return fail(MB_ERR_INVALID, "row-statistics epilogue needs N=%d, BN=256 or 128 (got N=%d BN=%d)", 128 * LN_PARTIALS, p.N, BN);
     if (BN == 256) return launch_gemm_bn<256>(h, ta, tb, p, epi, num_sms, st);
     if (BN == 128) return launch_gemm_bn<128>(h, ta, tb, p, epi, num_sms, st);
     if (BN == 64) return launch_gemm_bn<64>(h, ta, tb, p, epi, num_sms, st);

@@ -111,7 +111,7 @@ struct GemmCfg {
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // 128 / 256 / 512: powers of two
     static constexpr int NUM_THREADS = 384;
-    static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*statistics exchange*/;
 };
 
 // Exact-erf GELU (torch.nn.GELU() default, bert.py:29,413) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, the
@@ -275,7 +275,7 @@ struct EpiStage {
 template <int BN, int EPI, bool kTma = false, int NSPLIT = 2, bool kPre = false, bool kSV = false, bool kResS = false>
 __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, uint32_t taddr, int n_blk, int half,
                                         EpiStage stg = EpiStage{nullptr, nullptr, 0}, const uint4* res = nullptr,
-                                        const float* svec = nullptr) {
+                                        const float* svec = nullptr, float2* stats_xchg = nullptr) {
     constexpr bool kLnIn = EPI == EPI_LNIN_BF16 || EPI == EPI_LNIN_GELU_BF16 || EPI == EPI_LNIN_GELU_BF16_STATS || EPI == EPI_LNIN_F32_SEQ;
     constexpr bool kGelu = EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_F32 || EPI == EPI_LNIN_GELU_BF16 || EPI == EPI_LNIN_GELU_BF16_STATS;
     constexpr bool kStats = EPI == EPI_RES_LN_BF16_STATS || EPI == EPI_LNIN_GELU_BF16_STATS;
@@ -406,8 +406,19 @@ __device__ __forceinline__ void epi_run(const GemmParams& p, const EpiRow& er, u
 #pragma unroll 1
         for (int c = 0; c < COLS_PER_WARP; c += 32) chunk(c);
     }
-    if (kStats && row_ok && !GEMM_TIMING_NO_STATS) {   // slot = index of the warp's 128-column slab in the 1024-wide row
-        // (launches with a narrower warp slab are rejected on the host: launch_gemm requires BN == 256 for the STATS epilogues)
+    if constexpr (kStats && COLS_PER_WARP == 64) {
+        // 128-column tiles (the 1-CTA kernel at small M): the two warps of a lane quarter hold half a statistics slot each; the upper
+        // half hands its sums over through shared memory and the lower half stores lower + upper (a fixed order)
+        const int quarter = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31;
+        if (half == 1) stats_xchg[quarter * 32 + lane] = make_float2(st_sum + st_sum1, st_sq + st_sq1);
+        named_bar_sync(4 + quarter, 64);
+        if (half == 0 && row_ok && !GEMM_TIMING_NO_STATS) {
+            const float2 o = stats_xchg[quarter * 32 + lane];
+            p.stats_out[(size_t)row * LN_PARTIALS + (n_blk * BN) / 128] = make_float2((st_sum + st_sum1) + o.x, (st_sq + st_sq1) + o.y);
+        }
+        named_bar_sync(4 + quarter, 64);            // the slot is free for the next tile
+    } else if (kStats && row_ok && !GEMM_TIMING_NO_STATS) {   // slot = index of the warp's 128-column slab in the 1024-wide row
+        // (other slab widths are rejected on the host: launch_gemm)
         float2* so = p.stats_out + (size_t)row * LN_PARTIALS + (n_blk * BN + half * COLS_PER_WARP) / 128;
         so[0] = make_float2(st_sum + st_sum1, st_sq + st_sq1);
     }
@@ -430,6 +441,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     uint64_t* tmem_full = bars + 2 * STAGES;
     uint64_t* tmem_empty = bars + 2 * STAGES + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    float2* stats_xchg = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [4 lane quarters][32 rows]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_m = (p.M + BM - 1) / BM, num_n = p.N / BN;
@@ -498,7 +510,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             const EpiRow er = epi_prepare<EPI>(p, m_blk * BM + quarter * 32 + lane);
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
-            epi_run<BN, EPI>(p, er, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN, n_blk, half);
+            epi_run<BN, EPI>(p, er, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN, n_blk, half,
+                             EpiStage{nullptr, nullptr, 0}, nullptr, nullptr, stats_xchg);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -585,6 +598,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + C::EPI_WARPS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) GEMM_EV(3, 0, 0u, clock64());   // role 3 = kernel lifecycle: entry | set up | predecessor complete | work done
     // Warp roles.  The SM's warp schedulers favour the highest warp id among eligible warps, so with GEMM2_ROLES_HIGH the
     // single-thread TMA / MMA issuers sit above the eight epilogue warps instead of below them.
     constexpr int W_EPI0 = GEMM2_ROLES_HIGH ? 0 : 4, W_PROD = GEMM2_ROLES_HIGH ? 8 : 0, W_MMA = GEMM2_ROLES_HIGH ? 9 : 1,
@@ -613,6 +627,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
     cluster_sync_all();                              // barriers of both CTAs initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) GEMM_EV(3, 1, 0u, clock64());
     if (p.prefetch != nullptr && pair >= num_tiles && warp == W_PROD) {
         if (elect_one()) {  // ---------------- idle pair: its share of the next GEMM's weights -> L2, 4 KB per instruction
             const unsigned long long n_idle = 2ull * (unsigned)(num_pairs - num_tiles), idx = blockIdx.x - 2u * (unsigned)num_tiles;
@@ -627,6 +642,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
     }
     pdl_launch_dependents();
     pdl_wait();                                      // the predecessor's outputs (A rows, statistics, residual) are complete from here on
+    if (threadIdx.x == 0) GEMM_EV(3, 2, 0u, clock64());
 
     if (warp == W_PROD) {
         if (elect_one()) {  // ---------------- TMA producer (each CTA: its 128 A rows, its 128 of the 256 B rows)
@@ -745,6 +761,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
     __syncwarp();
     tc_fence_before();
     cluster_sync_all();                              // the leader's MMAs write the peer's TMEM: both done before dealloc
+    if (threadIdx.x == 0) GEMM_EV(3, 3, 0u, clock64());
     if (warp == W_ALLOC) {
         tc_fence_after();
         tmem_dealloc_2sm<512>(tmem_base);

@@ -136,7 +136,9 @@ def _gemm_ex(a, w, bias, vec2, residual, stats_in, epi, want_stats, seq_in=0, se
     return out, stats_out
 
 
-@pytest.mark.parametrize("M", [257, 1028, 2056])
+# M selects the schedule (api.cu launch_gemm): when 128 x 128 tiles fit in one wave (e.g. N = 1024 up to M = 2304) the 1-CTA kernel
+# with BN = 128 runs, else the CTA-pair kernel -- 5140 rows (20 sequences) is on the CTA-pair kernel for every N
+@pytest.mark.parametrize("M", [257, 1028, 2056, 5140])
 @pytest.mark.parametrize("epi,N", [(5, 3072), (6, 4096), (8, 1024)])
 def test_gemm_layernorm_folded_input(M, epi, N):
     """LN-in epilogues == Linear(LayerNorm(y)) [+ GELU] evaluated the plain way in fp64, with gamma / beta folded on the host
@@ -167,7 +169,7 @@ def test_gemm_layernorm_folded_input(M, epi, N):
         assert (st.sum(1) - want).abs().max().item() <= 1e-3 * want.abs().max().item()
 
 
-@pytest.mark.parametrize("M,K", [(257, 1024), (1028, 4096), (2056, 1024)])
+@pytest.mark.parametrize("M,K", [(257, 1024), (1028, 4096), (2056, 1024), (5140, 1024), (5140, 4096)])
 def test_gemm_residual_layernorm_stats(M, K):
     """Residual epilogue: out = A W^T + bias + LayerNorm(y_res) -> bf16, plus the partial statistics of the stored rows."""
     N = 1024
@@ -213,7 +215,8 @@ def test_gemm_layernorm_fold_stress(epi, N, ratio, outlier):
     """The LayerNorm-in epilogues (5: QKV, 6: MLP up, 8: head, 9: prediction layer) where the folding is fragile: rows whose mean
     is 10 / 100 standard deviations away from zero (cancellation in acc - mean*u and in E[y^2] - mean^2), an outlier channel,
     gains in [0.1, 5], biases up to +-3.  Reference = Linear(LayerNorm(y)) in fp64 on the same bf16 rows and folded bf16 weights."""
-    K, S, n_seq = 1024, 257, 4
+    K, S = 1024, 257
+    n_seq = 20 if epi == 8 else 4        # head (N = 1024): 20 sequences put it on the CTA-pair kernel like QKV / up at 4
     M = n_seq * S
     g = torch.Generator(device="cuda").manual_seed(int(epi * 1000 + ratio + 7 * outlier))
     y = _stress_rows(M, K, g, ratio, outlier)
@@ -244,10 +247,11 @@ def test_gemm_layernorm_fold_stress(epi, N, ratio, outlier):
 
 @pytest.mark.parametrize("ratio,outlier", [(10.0, False), (100.0, False), (10.0, True)])
 @pytest.mark.parametrize("K", [1024, 4096])
-def test_gemm_residual_fold_stress(K, ratio, outlier):
+@pytest.mark.parametrize("n_seq", [4, 20])
+def test_gemm_residual_fold_stress(K, ratio, outlier, n_seq):
     """Residual epilogue (7: out-projection, MLP down) on the same stressed rows: out = A W^T + b + LayerNorm(y_res), and the row
-    statistics it leaves for the next LayerNorm."""
-    N, M = 1024, 4 * 257
+    statistics it leaves for the next LayerNorm.  4 sequences: 1-CTA BN = 128 schedule; 20: CTA-pair kernel."""
+    N, M = 1024, n_seq * 257
     g = torch.Generator(device="cuda").manual_seed(int(K + ratio + 7 * outlier))
     a = torch.randn((M, K), device="cuda", generator=g).to(torch.bfloat16)
     W = (torch.randn((N, K), device="cuda", generator=g) * 0.03).to(torch.bfloat16)

@@ -102,6 +102,28 @@ def test_forward_matches_reference_golden(bits, golden_dir):
     assert (logits[:n] - logits[n:]).abs().max().item() > 1e-3
 
 
+def test_forward_large_batch_rows_match_golden(golden_dir):
+    """The golden sequences replicated to 24 rows of batch (M = 6168: every Linear on the CTA-pair kernel, where the fixture's own
+    2-4 sequences run the small-M schedule): each copy within the golden tolerance, and all copies bit-identical -- a row's
+    result does not depend on where in the batch it sits."""
+    g = np.load(os.path.join(golden_dir, "forward_12bit.npz"))
+    _, _, _, gen = models(12)
+    tok = torch.from_numpy(g["tokens"].astype(np.int64)).cuda()
+    labels, drop = torch.from_numpy(g["labels"]).cuda(), torch.from_numpy(g["drop"]).cuda()
+    n = tok.shape[0]
+    reps = (24 + n - 1) // n
+    logits = gen(tok.repeat(reps, 1, 1), labels.repeat(reps), drop.repeat(reps)).view(reps, n, *g["logits"].shape[1:])
+    ref = torch.from_numpy(g["logits"]).cuda()
+    d = (logits[0] - ref).abs()
+    print(f"forward 12bit, {reps * n} sequences: max abs {d.max().item():.4e} mean abs {d.mean().item():.4e}")
+    assert d.max().item() <= LOGIT_MAX_ABS and d.mean().item() <= LOGIT_MEAN_ABS
+    for r in range(1, reps):
+        assert torch.equal(logits[r], logits[0])
+    small = gen(tok, labels, drop)
+    print(f"   small-M schedule vs CTA-pair kernel on the same rows: max abs {(small - logits[0]).abs().max().item():.3e}")
+    assert (small - logits[0]).abs().max().item() <= LOGIT_MAX_ABS
+
+
 @pytest.mark.parametrize("bits", [10, 16, 18])
 def test_forward_other_shipped_widths_vs_oracle(bits):
     """The other shipped generator shapes (configs/generator/maskbit_generator_{10,16,18}bit.yaml: V = 32 / 256 / 512,
