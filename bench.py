@@ -479,17 +479,19 @@ def run_tokenizer(args):
         step(True)
     uuid = str(torch.cuda.get_device_properties(0).uuid)
     clocks = ClockSampler(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
-    tokenizer.profile_enable(True)
-    ms, launches = timed(args.steps, False)
-    prof = tokenizer.profile_read()
-    tokenizer.profile_enable(False)
+    ms, launches = timed(args.steps, False)                # value: no per-launch event pairs, chunk streams as in production
     clk = clocks.stop()
     ms_e2e, _ = timed(args.steps, True)
+    tokenizer.profile_enable(True)                         # third pass: per-class shares and the conv kernel's own time
+    timed(max(1, min(args.steps, args.profile_steps)) if args.profile_steps > 0 else 1, False)
+    prof = tokenizer.profile_read()
+    tokenizer.profile_enable(False)
     peaks = measured_peaks()
     n_img = B * args.steps
+    n_img_prof = B * (max(1, min(args.steps, args.profile_steps)) if args.profile_steps > 0 else 1)
     flops_img = 136.12e9 + F_DEC.get(args.bits, 185.97e9)
     conv_ms, conv_n = prof.get("dec_conv", (0.0, 0))
-    conv_flops = n_img * (flops_img - 0.45e9 - 0.028e9 - 0.45e9)          # minus conv_in / conv_out of both halves (CUDA-core kernels)
+    conv_flops = n_img_prof * (flops_img - 0.45e9 - 0.028e9 - 0.45e9)     # minus conv_in / conv_out of both halves (CUDA-core kernels)
     achieved = conv_flops / (conv_ms / 1000.0) / 1e12 if conv_ms else None
     gpu_ms = sum(v[0] for v in prof.values())
     line = {"metric": "images_per_sec", "value": n_img / (ms / 1000.0), "unit": "images/s", "n_gpus": 1, "steps": args.steps,
@@ -502,8 +504,10 @@ def run_tokenizer(args):
             "gpu_launches": int(launches), "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "conv_tcgen05_kernel (3 MMAs per product)", "achieved": achieved,
                          "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": (achieved / peaks["bf16_sustained"]) if achieved else None,
-                         "traffic": None, "peak_source": f"{peaks['source']} bf16_tflops_sustained", "launches": conv_n,
-                         "note": "algorithmic (single-pass) conv FLOPs; the tensor pipe executes 3x that"},
+                         "traffic": ncu_traffic("conv"), "peak_source": f"{peaks['source']} bf16_tflops_sustained", "launches": conv_n,
+                         "note": "reference-counted (single-pass, nearest-x2 + 3x3 unfused) conv FLOPs; the tensor pipe executes 3 MMAs per product, "
+                                 "and the four upsample convs run as 2x2-tap phase convs (16/36 of their counted products); "
+                                 "achieved and kernel_time_share come from a third pass with event pairs around every launch"},
             "kernel_time_share": {k: round(v[0] / gpu_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
     emit(line)
 

@@ -33,8 +33,16 @@ def launches(path):
         print(f"{v[1]:10.3f} ms {v[0]:5d}x  {100 * v[1] / tot:5.1f}%  avg {v[1] / v[0]:8.4f} ms  {k[:120]}")
 
 
+def raw_page(path):
+    """The `--page raw --csv` text of a capture: from the .ncu-rep, or a .csv already exported on the GPU box (reports with
+    --import-source run to 100+ MB, more than gpurun brings back)."""
+    if path.endswith(".csv"):
+        return open(path).read()
+    return subprocess.check_output(["ncu", "-i", path, "--page", "raw", "--csv"], text=True)
+
+
 def full(path):
-    raw = subprocess.check_output(["ncu", "-i", path, "--page", "raw", "--csv"], text=True)
+    raw = raw_page(path)
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     idx = [i for i, h in enumerate(hdr) if h in KEEP or h == "Kernel Name"]
@@ -44,19 +52,26 @@ def full(path):
             print(f"  {hdr[i]:85s} {r[i][:100]} {units[i]}")
 
 
-def traffic(path):
-    """dram bytes (read + write) per launch for each trunk kernel class of a full capture -> JSON on stdout
-    (committed as profiles/ncu_traffic.json and read by bench.py's roofline.traffic)."""
+def traffic(*paths):
+    """dram bytes (read + write) per launch for each trunk kernel class of one or more full captures -> JSON on stdout
+    (committed as profiles/ncu_traffic.json and read by bench.py's roofline.traffic).  `conv`: the mean over every captured
+    conv_tcgen05_kernel launch -- capture ALL conv launches of one tokenizer pass (encode + decode of one 32-image chunk) so that
+    the mean matches the mean launch bench.py --workload tokenizer times."""
     import json
-    raw = subprocess.check_output(["ncu", "-i", path, "--page", "raw", "--csv"], text=True)
-    rows = list(csv.reader(io.StringIO(raw)))
-    hdr, units = rows[0], rows[1]
-    ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    kinds = {"gemm2_bf16_tcgen05_kernel<5>": "gemm_qkv", "gemm2_bf16_tcgen05_kernel<6>": "gemm_up", "attention_tc_kernel": "attention"}
+    kinds = {"gemm2_bf16_tcgen05_kernel<5>": "gemm_qkv", "gemm2_bf16_tcgen05_kernel<6>": "gemm_up", "attention_tc_kernel": "attention",
+             "conv_tcgen05_kernel": "conv"}
     acc = collections.defaultdict(list)
     seen7 = 0
-    for r in rows[2:]:
+    allrows = []
+    for path in paths:
+        raw = raw_page(path)
+        rows = list(csv.reader(io.StringIO(raw)))
+        hdr, units = rows[0], rows[1]
+        ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        for r in rows[2:]:
+            allrows.append((r, ki, ri, wi, units))
+    for r, ki, ri, wi, units in allrows:
         name = re.sub(r"\(int\)", "", r[ki])
         b = float(r[ri].replace(",", "")) * scale[units[ri]] + float(r[wi].replace(",", "")) * scale[units[wi]]
         kind = next((v for k, v in kinds.items() if k in name), None)
@@ -66,9 +81,9 @@ def traffic(path):
         if kind:
             acc[kind].append(b)
     out = {k: {"dram_bytes_per_launch": sum(v) / len(v), "launches_captured": len(v)} for k, v in acc.items()}
-    out["_source"] = f"ncu --set full --clock-control none capture {path} (profiles/run_profile.sh), B=256 -> 512 sequences per forward"
+    out["_source"] = f"ncu --set full --clock-control none captures {', '.join(paths)} (profiles/run_profile_r02.sh); trunk: B=256 -> 512 sequences per forward; conv: one 32-image tokenizer pass"
     print(json.dumps(out, indent=1))
 
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
