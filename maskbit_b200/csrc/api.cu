@@ -1103,20 +1103,8 @@ extern "C" int mb_combine_tokens(mb_handle* h, const int64_t* tokens, int B, int
 
 // ------------------------------------------------------------------------------------------------ decoder
 static const int kDecChunk = 32;
-static int ensure_dec_ws(mb_handle* h, int nb, int sets) {
-    if (nb <= h->dec_cap && sets <= h->dec_sets) { use_dec_ws(h, 0); return 0; }
-    CU_TRY(cudaDeviceSynchronize());
-    if (sets < h->dec_sets) sets = h->dec_sets;
-    if (nb < h->dec_cap) nb = h->dec_cap;
-    free_dec_ws(h);
-    if (sets > 1 && !h->dstream[0]) {
-        for (int i = 0; i < 2; ++i) {
-            CU_TRY(cudaStreamCreateWithFlags(&h->dstream[i], cudaStreamNonBlocking));
-            CU_TRY(cudaEventCreateWithFlags(&h->dev_join[i], cudaEventDisableTiming));
-        }
-        CU_TRY(cudaEventCreateWithFlags(&h->dev_fork, cudaEventDisableTiming));
-    }
-  for (int set = 0; set < sets; ++set) {
+// one workspace set for `nb` images into the handle's current-set fields
+static int alloc_dec_set(mb_handle* h, int nb) {
     const mb_config& c = h->cfg;
     const int P = (int)lround(sqrt((double)c.seq_len));
     size_t max_elems = 0;
@@ -1155,9 +1143,29 @@ static int ensure_dec_ws(mb_handle* h, int nb, int sets) {
     }
     MB_TRY(dev_alloc(h, &h->act_hi, max_pad * nb, false));
     MB_TRY(dev_alloc(h, &h->act_lo, max_pad * nb, false));
-    save_dec_ws(h, set);
-    h->dec_sets = set + 1;
-  }
+    return 0;
+}
+static int ensure_dec_ws(mb_handle* h, int nb, int sets) {
+    if (nb <= h->dec_cap && sets <= h->dec_sets) { use_dec_ws(h, 0); return 0; }
+    CU_TRY(cudaDeviceSynchronize());
+    if (sets < h->dec_sets) sets = h->dec_sets;
+    if (nb < h->dec_cap) nb = h->dec_cap;
+    free_dec_ws(h);
+    if (sets > 1 && !h->dstream[0]) {
+        for (int i = 0; i < 2; ++i) {
+            CU_TRY(cudaStreamCreateWithFlags(&h->dstream[i], cudaStreamNonBlocking));
+            CU_TRY(cudaEventCreateWithFlags(&h->dev_join[i], cudaEventDisableTiming));
+        }
+        CU_TRY(cudaEventCreateWithFlags(&h->dev_fork, cudaEventDisableTiming));
+    }
+    for (int set = 0; set < sets; ++set) {
+        h->dx = h->dt1 = h->dt2 = h->gn_scale = h->gn_shift = nullptr; h->gn_partial = nullptr; h->gn_box = nullptr;
+        h->act_hi = h->act_lo = nullptr;
+        const int rc = alloc_dec_set(h, nb);
+        save_dec_ws(h, set);                 // also after a failed allocation: free_dec_ws releases what the set did get
+        h->dec_sets = set + 1;
+        if (rc) { free_dec_ws(h); return rc; }
+    }
     use_dec_ws(h, 0);
     h->dec_cap = nb;
     return 0;
@@ -1165,7 +1173,7 @@ static int ensure_dec_ws(mb_handle* h, int nb, int sets) {
 // Chunk loop of the decoder / encoder: chunk i runs on the handle's stream i & 1 with workspace set i & 1 (fork from / join into the
 // caller's stream by events), or everything on the caller's stream when there is a single chunk.
 struct ChunkStreams {
-    mb_handle* h; cudaStream_t caller; bool split; int used = 0;
+    mb_handle* h; cudaStream_t caller; bool split;
     ChunkStreams(mb_handle* h_, cudaStream_t st, int chunks) : h(h_), caller(st), split(chunks > 1 && g_dec_overlap && h_->dec_sets > 1 && !h_->profiling) {}
     int begin() {
         if (!split) return 0;

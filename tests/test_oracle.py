@@ -292,3 +292,28 @@ def test_training_forward_half_matches_reference(golden_dir):
                 assert np.allclose(got, want, rtol=1e-6, atol=1e-7), (v, mode, smooth, got, want)
     with pytest.raises(ValueError):
         O.get_mask_tokens(torch.zeros((1, 4, 2), dtype=torch.int64), 64, mode="root")
+
+
+def test_upsample_conv_phase_fold_identity():
+    """The identity the CUDA decoder's upsample convs rely on (csrc/api.cu pack_conv_up4_kernel, csrc/conv_tcgen05.cuh phases == 4):
+    nearest x2 followed by a SAME 3x3 conv (autoencoder.py:224-225) equals, for output pixel (2y+py, 2x+px), a 2x2-tap conv over the
+    zero-padded low-resolution input whose tap (a, b) reads pixel (y + a + py - 1, x + b + px - 1) with the 3x3 taps that land on that
+    source pixel summed (rows {0}, {1,2} for py = 0 and {0,1}, {2} for py = 1; columns alike).  fp64, so equality is to rounding."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn((2, 8, 6, 6), dtype=torch.float64, generator=g)
+    w = torch.randn((5, 8, 3, 3), dtype=torch.float64, generator=g)
+    b = torch.randn((5,), dtype=torch.float64, generator=g)
+    ref = torch.nn.functional.conv2d(torch.nn.functional.interpolate(x, scale_factor=2.0, mode="nearest"), w, b, padding=1)
+    taps = {(0, 0): [0], (0, 1): [1, 2], (1, 0): [0, 1], (1, 1): [2]}
+    xp = torch.nn.functional.pad(x, (1, 1, 1, 1))
+    H = x.shape[2]
+    out = torch.empty_like(ref)
+    for py in range(2):
+        for px in range(2):
+            acc = b[None, :, None, None].expand(2, 5, H, H).clone()
+            for a in range(2):
+                for bb in range(2):
+                    wf = sum(w[:, :, ky, kx] for ky in taps[(py, a)] for kx in taps[(px, bb)])
+                    acc += torch.einsum("nchw,oc->nohw", xp[:, :, a + py:a + py + H, bb + px:bb + px + H], wf)
+            out[:, :, py::2, px::2] = acc
+    assert (out - ref).abs().max().item() < 1e-12
