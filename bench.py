@@ -81,6 +81,34 @@ def ncu_traffic(kind):
         return json.load(f).get(kind, {}).get("dram_bytes_per_launch")
 
 
+def other_kernel_rooflines(prof, prof_steps, seqs, peaks):
+    """The other four trunk kernel classes against the roofline that bounds each, from the same per-class event timing as
+    `roofline` (in-job, under the power cap): the three remaining GEMMs against the measured sustained bf16 peak, attention against
+    the measured HBM rate (its algorithmic bytes: the qkv rows once + the output rows)."""
+    out = {}
+    rows = prof_steps * sum(n * S for n in seqs)
+    for kind, n_out, k_in in (("gemm_qkv", 3 * D, D), ("gemm_out", D, D), ("gemm_down", D, MLP)):
+        ms, n = prof.get(kind, (0.0, 0))
+        if ms > 0:
+            tf = 2.0 * rows * n_out * k_in * DEPTH / (ms / 1000.0) / 1e12
+            out[kind] = {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": tf / peaks["bf16_sustained"], "avg_launch_ms": ms / n, "traffic": ncu_traffic(kind)}
+    ms, n = prof.get("attention", (0.0, 0))
+    if ms > 0 and peaks.get("hbm"):
+        gbs = rows * (3 * D + D) * 2.0 * DEPTH / (ms / 1000.0) / 1e9
+        out["attention"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                            "avg_launch_ms": ms / n, "traffic": ncu_traffic("attention"),
+                            "tensor_tflops": 4.0 * rows * S * D * DEPTH / (ms / 1000.0) / 1e12}
+    return out
+
+
+def safe_other_kernel_rooflines(*a):
+    try:
+        return other_kernel_rooflines(*a)
+    except Exception as e:      # an accounting slip here must never cost the bench line
+        return {"error": repr(e)}
+
+
 def library_sustained_tflops(torch, m, n, k, seconds=2.0):
     a = torch.randn((m, k), device="cuda").to(torch.bfloat16)
     w = torch.randn((n, k), device="cuda").to(torch.bfloat16)
@@ -414,6 +442,7 @@ def run_b200(args):
                          "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
                          "launches": up_n, "avg_launch_ms": (up_ms / up_n) if up_n else None,
                          "flops_per_launch": up_flops / up_n if up_n else None},
+            "roofline_other_kernels": safe_other_kernel_rooflines(prof, prof_steps, seqs, peaks),
             "ms_per_sampling_step": ms_per_step / T,
             "job_tflops": job_flops / (ms / 1000.0) / 1e12 / world,
             "job_roofline_frac": job_flops / (ms / 1000.0) / 1e12 / world / peak,
