@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: the GEMM_EPI7_PIPE variant this script compares was measured neutral and removed from the tree; kept as the record of how
+# profiles/r02_epi7_pipe_neutral.txt was made.
 # residual-epilogue pipelining (GEMM_EPI7_PIPE) off / on and the rewritten conv_out kernel: kernel tests, decode parity, isolated and
 # sustained GEMM timings, tokenizer bench -- one box
 mkdir -p gpurun_out
