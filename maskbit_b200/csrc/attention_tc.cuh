@@ -53,6 +53,12 @@
                             // reduction + degree-3 polynomial + exponent insert) instead of MUFU.EX2: the MUFU pipe (16 / clk / SM) is
                             // the floor of pass 2 (4.1 k clk per item); P is rounded to bf16 afterwards, the polynomial's 7.5e-5 is invisible
 #endif
+#ifndef ATC_SPLIT_S
+#define ATC_SPLIT_S 0       // 1: S_t as two N = 128 halves (keys 0..127 -> TMEM columns [0,128), keys 128..255 -> [128,256)).  The first
+                            // half of the NEXT item is issued right behind this item's P V MMAs (same thread: in order, and by then P in
+                            // [0,128) is consumed), i.e. while the epilogue still drains O from [128,192); only the second half waits for
+                            // t_free.  Takes half of the S latency off the warpgroup's serial chain.
+#endif
 #ifndef ATC_FASTMAX
 #define ATC_FASTMAX 0       // 1: no row-max pass.  Softmax is shift-invariant and P (bf16) / the row sum / O (fp32) have the fp32 exponent
                             // range, so any shift within ~2^100 of the true maximum gives the same result: rows are shifted by their
@@ -245,15 +251,41 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
         }
     } else if (warp == 1 || warp == 2) {
         if (elect_one()) {  // -------------------------------------------------------------- MMA issuers: warp 1 -> tile 0, warp 2 -> tile 1
-            constexpr uint32_t idesc_s = make_idesc(1, 128, 256);
+            constexpr uint32_t idesc_s = make_idesc(1, 128, 256); (void)idesc_s;
             constexpr uint32_t idesc_o = make_idesc(1, 128, 64) | (1u << 16);   // B (= V) is MN-major
             const int t = warp - 1;
             const uint32_t tr = tmem_base + t * 256;
+#if ATC_SPLIT_S
+            constexpr uint32_t idesc_sh = make_idesc(1, 128, 128);
+            bool sa_done = false;                                               // first half of S for item `it` already issued
+#endif
             for (int it = k0; it < k1; ++it) {
                 const int st = it & 1;
                 const uint32_t sq = smem0 + st * ATC_STAGE_BYTES, sk = sq + ATC_TILE_BYTES, sv = sk + ATC_TILE_BYTES;
                 mbar_wait(&fullqk[st], (it >> 1) & 1);
                 ATC_EV(5 + t, 0, it);
+#if ATC_SPLIT_S
+                {                                                               // S_t = Q_t K^T in two key halves
+                    const uint64_t a = make_sdesc_k128(sq + t * 128 * 128);
+                    if (!sa_done) {                                             // first item of a round: the whole tile must be free
+                        mbar_wait(&t_free[t], (it & 1) ^ 1);
+                        tc_fence_after();
+                        const uint64_t b0 = make_sdesc_k128(sk);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_f16(tr, a + 2 * k, b0 + 2 * k, idesc_sh, k != 0);
+                    } else {
+                        mbar_wait(&t_free[t], (it & 1) ^ 1);                    // O of the previous item is out of columns [128,192)
+                        tc_fence_after();
+                    }
+                    ATC_EV(5 + t, 1, it);
+                    const uint64_t b1 = make_sdesc_k128(sk + 128 * 128);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(tr + 128, a + 2 * k, b1 + 2 * k, idesc_sh, k != 0);
+                    umma_commit(&s_full[t]);
+                    umma_commit(&emptyqk[st]);                                  // this tile's S MMAs have read Q and K
+                    ATC_EV(1, t, it);
+                }
+#else
                 mbar_wait(&t_free[t], (it & 1) ^ 1);
                 ATC_EV(5 + t, 1, it);
                 tc_fence_after();
@@ -265,6 +297,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
                     umma_commit(&emptyqk[st]);                                  // this tile's S MMAs have read Q and K
                     ATC_EV(1, t, it);
                 }
+#endif
                 mbar_wait(&p_full[t], it & 1);
                 ATC_EV(5 + t, 2, it);
                 mbar_wait(&fullv[st], (it >> 1) & 1);
@@ -278,6 +311,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_big, const __grid_con
                     umma_commit(&emptyv[st]);                                   // this tile's P V MMAs have read V
                     ATC_EV(1, 2 + t, it);
                 }
+#if ATC_SPLIT_S
+                sa_done = false;
+                if (it + 1 < k1) {                                              // next item's first S half, behind the P V MMAs
+                    const int sn = (it + 1) & 1;
+                    const uint32_t sqn = smem0 + sn * ATC_STAGE_BYTES;
+                    mbar_wait(&fullqk[sn], ((it + 1) >> 1) & 1);
+                    tc_fence_after();
+                    const uint64_t a = make_sdesc_k128(sqn + t * 128 * 128), b0 = make_sdesc_k128(sqn + ATC_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(tr, a + 2 * k, b0 + 2 * k, idesc_sh, k != 0);
+                    sa_done = true;
+                }
+#endif
             }
         }
     } else if (warp == 3) {  // -------------------------------------------------------------- the class-token query row
