@@ -165,3 +165,26 @@ def test_bench_flop_accounting_matches_survey():
     assert bench.f_fwd(12) == 162_328_313_856 and bench.f_fwd(14) == 162_396_733_440
     assert abs(bench.f_img(12, 64) - 20.964e12) < 0.001e12 and abs(bench.f_img(12, 8) - 2.783e12) < 0.001e12
     assert abs(2 * 256 * bench.f_fwd(12) - 83.11e12) < 0.01e12          # transformer-step roofline numerator at B = 256
+
+
+def test_bench_other_kernel_rooflines_accounting():
+    """bench.py's per-kernel rooflines: with every GEMM class given the time its FLOPs take at exactly 1000 TFLOP/s and attention the
+    time its algorithmic bytes take at 1000 GB/s, the helper must report those rates; per sequence and layer the four GEMMs add up
+    to the 6.47 GFLOP DESIGN.md section 4 states."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    S, D, MLP, DEPTH = bench.S, bench.D, bench.MLP, bench.DEPTH
+    per_seq = 2 * S * (3 * D * D + D * D + 2 * D * MLP)
+    assert abs(per_seq - 6.47e9) < 0.01e9
+    seqs, steps = [512] * 61 + [256] * 3, 2
+    rows = steps * sum(n * S for n in seqs)
+    prof = {"gemm_qkv": (2.0 * rows * 3 * D * D * DEPTH / 1e12, 10), "gemm_out": (2.0 * rows * D * D * DEPTH / 1e12, 10),
+            "gemm_down": (2.0 * rows * D * MLP * DEPTH / 1e12, 10), "attention": (rows * 4 * D * 2.0 * DEPTH / 1e9, 10)}
+    peaks = dict(bf16_sustained=1358.3, bf16_burst=1601.2, hbm=6549.8, source="measured")
+    out = bench.other_kernel_rooflines(prof, steps, seqs, peaks)
+    for k in ("gemm_qkv", "gemm_out", "gemm_down"):
+        assert abs(out[k]["achieved"] - 1000.0) < 1e-6 and out[k]["unit"] == "TFLOP/s" and abs(out[k]["frac"] - 1000.0 / 1358.3) < 1e-9
+    assert abs(out["attention"]["achieved"] - 1000.0) < 1e-6 and out["attention"]["bound"] == "hbm"
+    assert "error" not in bench.safe_other_kernel_rooflines(prof, steps, seqs, peaks)
