@@ -121,6 +121,9 @@ __global__ void __launch_bounds__(512) select_step_kernel(SelectParams p) {
     const uint32_t crank = cs > 1 ? cluster_ctarank() : 0u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int V = VPL * 32;
+    // Cluster form: a CTA's shared memory may only be written remotely once that CTA is known to have started.  Arrive here, wait
+    // just before the slot loop (the first DSMEM store) -- the barrier's latency hides behind the mask count.
+    if (cs > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");    // programmatic dependent launch (ptx.cuh): the logits come from
     asm volatile("griddepcontrol.wait;" ::: "memory");                 // the prediction-layer GEMM
 
@@ -132,6 +135,7 @@ __global__ void __launch_bounds__(512) select_step_kernel(SelectParams p) {
     cnt = __reduce_add_sync(0xffffffffu, cnt);
     if (lane == 0 && cnt) atomicAdd(&s_count, cnt);
 
+    if (cs > 1) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");    // every CTA of the cluster is running
     for (int s = (int)crank * nwarps + warp; s < slots; s += nwarps * cs) {
         const int pos = s / p.m, g = s - pos * p.m;
         const size_t off = (((size_t)b * p.seq_stride + pos) * p.m + g) * V;
